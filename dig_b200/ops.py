@@ -1,0 +1,126 @@
+"""ctypes binding of the dig_b200 C-ABI (include/dig_b200.h).
+
+PyTorch is used only to own device memory and streams: every function here takes torch CUDA tensors,
+passes their `data_ptr()` and sizes through the C-ABI and enqueues hand-written sm_100a kernels on the
+current stream.  There is no fallback: a missing library or a failing call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_LIB_NAME = "libdig_b200.so"
+_lib = None
+
+
+class DigError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+class _Gemm(ctypes.Structure):
+    _fields_ = [
+        ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
+        ("A", ctypes.c_void_p), ("lda", ctypes.c_int64), ("a_mn_major", ctypes.c_int32),
+        ("B", ctypes.c_void_p), ("ldb", ctypes.c_int64), ("b_mn_major", ctypes.c_int32),
+        ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64), ("out_fp32", ctypes.c_int32),
+        ("bias", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64),
+        ("res_row_mod", ctypes.c_int64),
+        ("row_mask", ctypes.c_void_p), ("row_mask_value", ctypes.c_void_p),
+        ("epilogue", ctypes.c_int32),
+        ("aux", ctypes.c_void_p), ("ldaux", ctypes.c_int64),
+        ("alpha", ctypes.c_float),
+        ("split_k", ctypes.c_int32),
+    ]
+
+
+EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_RELU_MASK = 0, 1, 2, 3
+
+
+def load():
+    """Load the in-tree shared library; raises DigError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.isfile(path):
+        raise DigError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(dig_b200 has no CPU / eager fallback)" % path)
+    lib = ctypes.CDLL(path)
+    lib.dig_last_error.restype = ctypes.c_char_p
+    lib.dig_version.restype = ctypes.c_int
+    lib.dig_sm.restype = ctypes.c_int
+    lib.dig_gemm.argtypes = [ctypes.POINTER(_Gemm), ctypes.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise DigError("%s failed (%d): %s" % (what, rc, load().dig_last_error().decode()))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise DigError("%s must be a CUDA tensor (dig_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise DigError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.stride(-1) != 1:
+        raise DigError("%s must have a contiguous last dimension" % name)
+
+
+def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=None, res_row_mod=0, row_mask=None,
+         row_mask_value=None, epilogue=EPI_LINEAR, aux=None, alpha=1.0, split_k=1):
+    """out[M,N] = epilogue(alpha * A.B^T) on tcgen05 (see include/dig_b200.h).
+
+    a: bf16 [M,K] (K-major) or [K,M] (a_mn_major); b: bf16 [N,K] or [K,N] (b_mn_major);
+    out: bf16 or fp32 [M,N].  All 2-D, last dim contiguous.
+    """
+    _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
+    if a_mn_major:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn_major:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    if K != Kb or tuple(out.shape) != (M, N):
+        raise DigError("gemm shape mismatch: a%s b%s out%s" % (tuple(a.shape), tuple(b.shape), tuple(out.shape)))
+    g = _Gemm()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda, g.a_mn_major = a.data_ptr(), a.stride(0), int(a_mn_major)
+    g.B, g.ldb, g.b_mn_major = b.data_ptr(), b.stride(0), int(b_mn_major)
+    g.out, g.ldo, g.out_fp32 = out.data_ptr(), out.stride(0), int(out.dtype == torch.float32)
+    if out.dtype not in (torch.float32, torch.bfloat16):
+        raise DigError("out must be fp32 or bf16")
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+        g.bias = bias.data_ptr()
+    if residual is not None:
+        _req(residual, torch.float32, "residual")
+        g.residual, g.ldr = residual.data_ptr(), residual.stride(0)
+    g.res_row_mod = res_row_mod
+    if row_mask is not None:
+        _req(row_mask, torch.uint8, "row_mask"); _req(row_mask_value, torch.float32, "row_mask_value")
+        g.row_mask, g.row_mask_value = row_mask.data_ptr(), row_mask_value.data_ptr()
+    g.epilogue = epilogue
+    if aux is not None:
+        _req(aux, torch.bfloat16, "aux")
+        g.aux, g.ldaux = aux.data_ptr(), aux.stride(0)
+    g.alpha = alpha
+    g.split_k = split_k
+    _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")
+    return out
