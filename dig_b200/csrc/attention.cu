@@ -1,0 +1,435 @@
+// dig_b200 -- fused multi-head self-attention over the 256 patch tokens of a 32x128 crop (head_dim 64).
+//
+// Replaces modeling_finetune.py:97-118 of the reference (q*scale, q@k^T, softmax, @v -- two cuBLAS bmm and
+// an ATen softmax that materialise a [S,h,256,256] score tensor in HBM) and its autograd backward.  Scores
+// never leave the SM: S = Q.K^T is accumulated in TMEM by tcgen05.mma, each thread owns one query row for
+// the softmax (a whole row of 256 keys is resident, so no online rescaling), P goes back to the tensor core
+// as a bf16 operand (from TMEM in the forward, from swizzled shared memory in the backward).
+//
+// Layout: qkv is the QKV projection output [S*256, 3*d] bf16 (q | k | v, each head a 64-column slice, exactly
+// the memory order F:93-95 reshapes); TMA pulls the per-head tiles straight out of it, so there is no
+// permute/contiguous pass.  The context is written as [S*256, d] bf16, ready for the output projection.
+#include "common.cuh"
+#include "../../include/dig_b200.h"
+
+namespace dig {
+
+static constexpr int kTok = 256;  // tokens per sequence (8 x 32 patch grid)
+static constexpr int kHd = 64;    // head dim
+static constexpr float kLog2e = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------------
+// forward: one CTA per (sequence, head, 128-query tile)
+// ------------------------------------------------------------------------------------------------
+template <bool P_TMEM>
+__global__ void __launch_bounds__(160, P_TMEM ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int heads,
+                float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                 // 128 x 64 bf16, K-major SW128               16 KB
+  uint8_t* sK = smem + 16384;         // 256 x 64 bf16, K-major SW128 (B of Q.K^T)   32 KB
+  uint8_t* sV = smem + 49152;         // 256 x 64 bf16, rows = keys -> MN-major B of P.V  32 KB
+  uint8_t* sP = smem + 81920;         // !P_TMEM: 4 x (128 x 64) bf16 K-major SW128   64 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920 + (P_TMEM ? 0 : 65536));
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x & 1;
+  const int head = (blockIdx.x >> 1) % heads;
+  const int seq = (blockIdx.x >> 1) / heads;
+  const int d = heads * kHd;
+  const int row0 = seq * kTok;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, 256);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  constexpr uint32_t kColO = 192;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_qk, 16384 + 32768);
+      tma_load_2d(sQ, &tm_qkv, bar_qk, head * kHd, row0 + qt * 128);
+      tma_load_2d(sK, &tm_qkv, bar_qk, d + head * kHd, row0);
+      tma_load_2d(sK + 16384, &tm_qkv, bar_qk, d + head * kHd, row0 + 128);
+      mbar_expect_tx(bar_v, 32768);
+      tma_load_2d(sV, &tm_qkv, bar_v, 2 * d + head * kHd, row0);
+      tma_load_2d(sV + 16384, &tm_qkv, bar_v, 2 * d + head * kHd, row0 + 128);
+
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
+#pragma unroll
+      for (int k = 0; k < kHd / 16; ++k)
+        tc_mma_ss(tmem, make_sdesc_sw128(smem_u32(sQ) + k * 32, 16, 1024), make_sdesc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s,
+                  k > 0);
+      tc_commit(bar_s);
+
+      mbar_wait(bar_p, 0);
+      mbar_wait(bar_v, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+#pragma unroll
+      for (int k = 0; k < kTok / 16; ++k) {
+        const uint64_t dv = make_sdesc_sw128(smem_u32(sV) + k * 2048, 8192, 1024);
+        if (P_TMEM) tc_mma_ts(tmem + kColO, tmem + k * 8, dv, idesc_o, k > 0);
+        else
+          tc_mma_ss(tmem + kColO, make_sdesc_sw128(smem_u32(sP) + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), dv, idesc_o, k > 0);
+      }
+      tc_commit(bar_o);
+    }
+  } else {
+    // softmax warps: thread t owns query row t of this tile == TMEM lane t
+    const int t = threadIdx.x;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < kTok; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tl + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    const float mb = mx * sl2;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < kTok; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tl + c, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float p0 = exp2f(fmaf(__uint_as_float(v[j]), sl2, -mb));
+        const float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), sl2, -mb));
+        sum += p0 + p1;
+        pk[j >> 1] = pack_bf16(p0, p1);
+      }
+      if (P_TMEM) {
+        tmem_st16(tl + (c >> 1), pk);
+      } else {
+        uint8_t* base = sP + (c >> 6) * 16384;
+        const uint32_t ch0 = (c & 63) >> 3;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          *reinterpret_cast<uint4*>(base + sw128_offset(t, ch0 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+      }
+    }
+    if (P_TMEM) tmem_st_wait();
+    else fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+    const long long grow = (long long)row0 + qt * 128 + t;
+    __nv_bfloat16* o = out + grow * d + head * kHd;
+#pragma unroll
+    for (int c = 0; c < kHd; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tl + kColO + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 p;
+        p.x = pack_bf16(__uint_as_float(v[j + 0]) * inv, __uint_as_float(v[j + 1]) * inv);
+        p.y = pack_bf16(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+        p.z = pack_bf16(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+        p.w = pack_bf16(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(o + c + j) = p;
+      }
+    }
+    if (lse != nullptr) lse[((long long)seq * heads + head) * kTok + qt * 128 + t] = mx * scale + logf(sum);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: one CTA per (sequence, head); loops key half j x query half i
+//   S = Q_i K_j^T, dP = dO_i V_j^T  (TMEM)  ->  P = exp(scale*S - lse), dS = scale * P o (dP - D)  (threads)
+//   dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j   (TMEM accumulators)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                __nv_bfloat16* __restrict__ dqkv, int heads, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;            // 256 x 64, rows = tokens (two 128-row tiles of 16 KB)
+  uint8_t* sK = smem + 32768;
+  uint8_t* sV = smem + 65536;
+  uint8_t* sdO = smem + 98304;
+  uint8_t* sP = smem + 131072;   // [128 queries x 128 keys] as two 64-key column chunks of 16 KB
+  uint8_t* sdS = smem + 163840;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 196608);
+  uint64_t* bar_ld = bars + 0;
+  uint64_t* bar_sdp = bars + 1;
+  uint64_t* bar_pds = bars + 2;
+  uint64_t* bar_mma = bars + 3;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x % heads;
+  const int seq = blockIdx.x / heads;
+  const int d = heads * kHd;
+  const int row0 = seq * kTok;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      mbar_init(bar_ld, 1);
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_pds, 128);
+      mbar_init(bar_mma, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  constexpr uint32_t cS = 0, cdP = 128, cdV = 256, cdK = 320, cdQ = 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_ld, 4 * 32768);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        tma_load_2d(sQ + r * 16384, &tm_qkv, bar_ld, head * kHd, row0 + r * 128);
+        tma_load_2d(sK + r * 16384, &tm_qkv, bar_ld, d + head * kHd, row0 + r * 128);
+        tma_load_2d(sV + r * 16384, &tm_qkv, bar_ld, 2 * d + head * kHd, row0 + r * 128);
+        tma_load_2d(sdO + r * 16384, &tm_do, bar_ld, head * kHd, row0 + r * 128);
+      }
+      mbar_wait(bar_ld, 0);
+      tc_fence_after();
+      constexpr uint32_t id_s = make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t id_tt = make_idesc_bf16(128, 64, true, true);   // dV, dK: A = P^T / dS^T (MN-major), B MN-major
+      constexpr uint32_t id_q = make_idesc_bf16(128, 64, false, true);   // dQ: A = dS (K-major), B = K (MN-major)
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), adO = smem_u32(sdO), aP = smem_u32(sP),
+                     adS = smem_u32(sdS);
+      int it = 0;
+      for (int j = 0; j < 2; ++j) {
+        for (int i = 0; i < 2; ++i, ++it) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_ss(tmem + cS, make_sdesc_sw128(aQ + i * 16384 + k * 32, 16, 1024), make_sdesc_sw128(aK + j * 16384 + k * 32, 16, 1024),
+                      id_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_ss(tmem + cdP, make_sdesc_sw128(adO + i * 16384 + k * 32, 16, 1024), make_sdesc_sw128(aV + j * 16384 + k * 32, 16, 1024),
+                      id_s, k > 0);
+          tc_commit(bar_sdp);
+          mbar_wait(bar_pds, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
+            tc_mma_ss(tmem + cdV, make_sdesc_sw128(aP + k * 2048, 16384, 1024), make_sdesc_sw128(adO + i * 16384 + k * 2048, 8192, 1024),
+                      id_tt, (i > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
+            tc_mma_ss(tmem + cdK, make_sdesc_sw128(adS + k * 2048, 16384, 1024), make_sdesc_sw128(aQ + i * 16384 + k * 2048, 8192, 1024),
+                      id_tt, (i > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // dQ_i += dS K_j     (reduction over 128 keys)
+            tc_mma_ss(tmem + cdQ + i * 64, make_sdesc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_sdesc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0));
+          tc_commit(bar_mma);
+        }
+      }
+    }
+  } else {
+    const int t = threadIdx.x;  // row within a 128-token tile == TMEM lane
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    // D_i = rowsum(dO o O), lse_i for the two query rows this thread owns
+    float Dr[2], Lr[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long grow = (long long)row0 + i * 128 + t;
+      const uint4* po = reinterpret_cast<const uint4*>(out + grow * d + head * kHd);
+      const uint4* pd = reinterpret_cast<const uint4*>(dout + grow * d + head * kHd);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 a = __ldg(po + c), b = __ldg(pd + c);
+        acc += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
+               bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+      }
+      Dr[i] = acc;
+      Lr[i] = lse[((long long)seq * heads + head) * kTok + i * 128 + t] * kLog2e;
+    }
+    int mma_seen = 0;
+    int it = 0;
+    for (int j = 0; j < 2; ++j) {
+      for (int i = 0; i < 2; ++i, ++it) {
+        mbar_wait(bar_sdp, it & 1);
+        tc_fence_after();
+        while (mma_seen < it) { mbar_wait(bar_mma, mma_seen & 1); ++mma_seen; }  // P/dS buffers free again
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t s[32], g[32];
+          tmem_ld32(tl + cS + c, s);
+          tmem_ld32(tl + cdP + c, g);
+          tmem_ld_wait();
+          uint32_t pp[16], ds[16];
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            const float p0 = exp2f(fmaf(__uint_as_float(s[q]), sl2, -Lr[i]));
+            const float p1 = exp2f(fmaf(__uint_as_float(s[q + 1]), sl2, -Lr[i]));
+            const float d0 = p0 * (__uint_as_float(g[q]) - Dr[i]) * scale;
+            const float d1 = p1 * (__uint_as_float(g[q + 1]) - Dr[i]) * scale;
+            pp[q >> 1] = pack_bf16(p0, p1);
+            ds[q >> 1] = pack_bf16(d0, d1);
+          }
+          const uint32_t sub = (c >> 6) * 16384;
+          const uint32_t ch0 = (c & 63) >> 3;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t off = sub + sw128_offset(t, ch0 + jj);
+            *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[4 * jj], pp[4 * jj + 1], pp[4 * jj + 2], pp[4 * jj + 3]);
+            *reinterpret_cast<uint4*>(sdS + off) = make_uint4(ds[4 * jj], ds[4 * jj + 1], ds[4 * jj + 2], ds[4 * jj + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+        if (i == 1) {
+          while (mma_seen < it + 1) { mbar_wait(bar_mma, mma_seen & 1); ++mma_seen; }
+          tc_fence_after();
+          const long long grow = (long long)row0 + j * 128 + t;
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {  // 0: dV, 1: dK
+            __nv_bfloat16* o = dqkv + grow * (3 * d) + (which == 0 ? 2 * d : d) + head * kHd;
+#pragma unroll
+            for (int c = 0; c < kHd; c += 32) {
+              uint32_t v[32];
+              tmem_ld32(tl + (which == 0 ? cdV : cdK) + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 32; q += 8) {
+                uint4 p;
+                p.x = pack_bf16(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1]));
+                p.y = pack_bf16(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+                p.z = pack_bf16(__uint_as_float(v[q + 4]), __uint_as_float(v[q + 5]));
+                p.w = pack_bf16(__uint_as_float(v[q + 6]), __uint_as_float(v[q + 7]));
+                *reinterpret_cast<uint4*>(o + c + q) = p;
+              }
+            }
+          }
+          tc_fence_before();
+        }
+      }
+    }
+    // dQ for both query tiles (complete after the last commit, which the i==1 wait above has seen)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long grow = (long long)row0 + i * 128 + t;
+      __nv_bfloat16* o = dqkv + grow * (3 * d) + head * kHd;
+#pragma unroll
+      for (int c = 0; c < kHd; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tl + cdQ + i * 64 + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          uint4 p;
+          p.x = pack_bf16(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1]));
+          p.y = pack_bf16(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+          p.z = pack_bf16(__uint_as_float(v[q + 4]), __uint_as_float(v[q + 5]));
+          p.w = pack_bf16(__uint_as_float(v[q + 6]), __uint_as_float(v[q + 7]));
+          *reinterpret_cast<uint4*>(o + c + q) = p;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace dig
+
+extern "C" int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t num_seqs, int32_t heads, float scale,
+                                 int32_t p_in_smem, void* stream) {
+  using namespace dig;
+  DIG_REQUIRE(qkv && out, "dig_attention_fwd: null pointer");
+  DIG_REQUIRE(num_seqs > 0 && heads > 0, "dig_attention_fwd: empty problem");
+  const int d = heads * kHd;
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)num_seqs * kTok, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64);
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)(num_seqs * heads * 2);
+  if (!p_in_smem) {
+    const int smem = 81920 + 1024 + 128;
+    static bool set = false;
+    if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    attn_fwd_kernel<true><<<grid, 160, smem, s>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), lse, heads, scale);
+  } else {
+    const int smem = 81920 + 65536 + 1024 + 128;
+    static bool set = false;
+    if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    attn_fwd_kernel<false><<<grid, 160, smem, s>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), lse, heads, scale);
+  }
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int64_t num_seqs,
+                                 int32_t heads, float scale, void* stream) {
+  using namespace dig;
+  DIG_REQUIRE(qkv && out && dout && lse && dqkv, "dig_attention_bwd: null pointer");
+  DIG_REQUIRE(num_seqs > 0 && heads > 0, "dig_attention_bwd: empty problem");
+  const int d = heads * kHd;
+  CUtensorMap tq, td;
+  int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)num_seqs * kTok, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&td, dout, (uint64_t)num_seqs * kTok, (uint64_t)d, (uint64_t)d, 128, 64);
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int smem = 196608 + 1024 + 128;
+  static bool set = false;
+  if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  attn_bwd_kernel<<<(int)(num_seqs * heads), 160, smem, s>>>(tq, td, reinterpret_cast<const __nv_bfloat16*>(out),
+                                                            reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+                                                            reinterpret_cast<__nv_bfloat16*>(dqkv), heads, scale);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

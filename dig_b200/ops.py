@@ -55,6 +55,9 @@ def load():
     lib.dig_version.restype = ctypes.c_int
     lib.dig_sm.restype = ctypes.c_int
     lib.dig_gemm.argtypes = [ctypes.POINTER(_Gemm), ctypes.c_void_p]
+    vp, i64, i32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+    lib.dig_attention_fwd.argtypes = [vp, vp, vp, i64, i32, f32, i32, vp]
+    lib.dig_attention_bwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, vp]
     _lib = lib
     return lib
 
@@ -124,3 +127,35 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
     g.split_k = split_k
     _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")
     return out
+
+
+def attention_fwd(qkv, out, lse, heads, scale, p_in_smem=False):
+    """Fused softmax(q k^T * scale) v over 256-token sequences (F:97-118). qkv bf16 [S*256, 3*heads*64]."""
+    _req(qkv, torch.bfloat16, "qkv"); _req(out, torch.bfloat16, "out")
+    d = heads * 64
+    rows = qkv.shape[0]
+    if qkv.shape[1] != 3 * d or rows % 256 or tuple(out.shape) != (rows, d) or not qkv.is_contiguous() or not out.is_contiguous():
+        raise DigError("attention_fwd: bad shapes qkv%s out%s heads=%d" % (tuple(qkv.shape), tuple(out.shape), heads))
+    if lse is not None:
+        _req(lse, torch.float32, "lse")
+        if lse.numel() != rows // 256 * heads * 256:
+            raise DigError("attention_fwd: lse must hold [S, heads, 256]")
+    _check(load().dig_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), rows // 256, heads, scale, int(p_in_smem), _stream()),
+           "dig_attention_fwd")
+    return out
+
+
+def attention_bwd(qkv, out, dout, lse, dqkv, heads, scale):
+    """Gradient of attention_fwd w.r.t. qkv."""
+    for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
+        _req(t, torch.bfloat16, n)
+        if not t.is_contiguous():
+            raise DigError("attention_bwd: %s must be contiguous" % n)
+    _req(lse, torch.float32, "lse")
+    d = heads * 64
+    rows = qkv.shape[0]
+    if qkv.shape != dqkv.shape or out.shape != dout.shape or qkv.shape[1] != 3 * d or tuple(out.shape) != (rows, d) or rows % 256:
+        raise DigError("attention_bwd: bad shapes")
+    _check(load().dig_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), rows // 256, heads, scale, _stream()),
+           "dig_attention_bwd")
+    return dqkv

@@ -53,6 +53,18 @@ typedef struct dig_gemm {
 } dig_gemm_t;
 int dig_gemm(const dig_gemm_t* g, void* stream);
 
+/* ---- fused attention over the 256 patch tokens, head_dim 64 --------------------------------------
+ * Replaces F:97-118 (q*scale, q@k^T, softmax, attn@v) and its autograd backward.
+ * qkv  : bf16 [num_seqs*256, 3*heads*64]  (q | k | v; head h = columns h*64..h*64+63 of each third, F:93-95)
+ * out  : bf16 [num_seqs*256, heads*64]    context, token-major (the layout F:118 transposes back to)
+ * lse  : fp32 [num_seqs, heads, 256]      natural-log-sum-exp of the scaled scores (may be NULL in forward)
+ * p_in_smem: 0 = probabilities fed back to the tensor core from TMEM, 1 = from shared memory.      */
+int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t num_seqs, int32_t heads, float scale,
+                      int32_t p_in_smem, void* stream);
+/* dqkv : bf16 [num_seqs*256, 3*heads*64] gradient w.r.t. qkv given dout (bf16, layout of out).      */
+int dig_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                      int64_t num_seqs, int32_t heads, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,8 +34,9 @@ for amn in (False, True):
         run(128, 128, 64, amn, bmn)
         run(256, 384, 384, amn, bmn)
         run(1024, 1152, 384, amn, bmn, torch.bfloat16)
-        run(358, 192, 384, amn, bmn)       # M tail, BN=64 path
-        run(358, 48 + 16, 192, amn, bmn)
+        Mt = 360 if amn else 358           # MN-major A needs lda % 8 == 0
+        run(Mt, 192, 384, amn, bmn)        # M tail, BN=64 path
+        run(Mt, 48 + 16, 192, amn, bmn)
         run(384, 1152, 4096, amn, bmn, split_k=8)
 run(65536, 1152, 384, False, False, torch.bfloat16)
 run(1152, 384, 65536, True, True, split_k=16)
