@@ -1,0 +1,226 @@
+// dig_b200 -- loss-side kernels, all fp32 (the InfoNCE logits carry a 1/T = 5 gain, so they stay out of bf16):
+//   L2 row normalisation fwd/bwd (F.normalize, M:446-447), a small fp32 tiled GEMM for the q.k^T logits and their
+//   gradient (torch.einsum, M:451), the fused row-wise cross-entropy / top-k accuracy (M:453-461, M:593-625) and the
+//   masked-pixel MSE with on-the-fly target patchify (E:85-111, E:141).
+#include "common.cuh"
+#include "../../include/dig_b200.h"
+
+namespace dig {
+
+// ---- L2 normalise: warp per row ---------------------------------------------------------------------
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_norm, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = x[row * C + c]; s += v * v; }
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int c = lane; c < C; c += 32) y[row * C + c] = x[row * C + c] * inv;
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+}
+
+// dx = (dy - y * <y, dy>) * inv_norm * gscale[0]
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm,
+                                  const float* __restrict__ gscale, float* __restrict__ dx, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += y[row * C + c] * dy[row * C + c];
+  s = warp_sum(s);
+  const float k = inv_norm[row] * (gscale ? gscale[0] : 1.f);
+  for (int c = lane; c < C; c += 32) dx[row * C + c] = (dy[row * C + c] - y[row * C + c] * s) * k;
+}
+
+// ---- fp32 GEMM on CUDA cores: C[M,N] = alpha * A[M,K] . (B_NT ? B[N,K]^T : B[K,N]) ----------------------
+template <bool B_NT>
+__global__ void __launch_bounds__(256)
+sgemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, float alpha) {
+  __shared__ float sA[16][64 + 4];
+  __shared__ float sB[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int kk = i & 15, mm = i >> 4;
+      const int gm = m0 + mm, gk = k0 + kk;
+      sA[kk][mm] = (gm < M && gk < K) ? A[(long long)gm * K + gk] : 0.f;
+    }
+    if (B_NT) {
+      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        const int kk = i & 15, nn = i >> 4;
+        const int gn = n0 + nn, gk = k0 + kk;
+        sB[kk][nn] = (gn < N && gk < K) ? B[(long long)gn * K + gk] : 0.f;
+      }
+    } else {
+      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        const int nn = i & 63, kk = i >> 6;
+        const int gn = n0 + nn, gk = k0 + kk;
+        sB[kk][nn] = (gn < N && gk < K) ? B[(long long)gk * N + gn] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) C[(long long)gm * N + gn] = acc[i][j] * alpha;
+    }
+}
+
+// ---- InfoNCE row pass: one block per query row over logits[Q, Nk] (already divided by T) ---------------
+// result[0] += (lse - z_label) * 2T/Q ; result[1] += 100/Q * [rank<1] ; result[2] += 100/Q * [rank<5]
+// logits row is overwritten with d(loss)/d(q.k) = (2/Q) * (softmax - onehot)
+__global__ void __launch_bounds__(256)
+infonce_rows_kernel(float* __restrict__ logits, int Q, int Nk, long long label_offset, float T, float* __restrict__ result) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int row = blockIdx.x;
+  float* z = logits + (long long)row * Nk;
+  const int label = (int)(label_offset + row);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < Nk; c += 256) mx = fmaxf(mx, z[c]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bcast = m; }
+  __syncthreads();
+  mx = bcast;
+  const float zl = z[label];
+  float s = 0.f, rank = 0.f;
+  for (int c = threadIdx.x; c < Nk; c += 256) {
+    const float v = z[c];
+    s += __expf(v - mx);
+    rank += (v > zl) ? 1.f : 0.f;
+  }
+  s = warp_sum(s);
+  rank = warp_sum(rank);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; bcast = t; }
+  __syncthreads();
+  const float sum = bcast;
+  __syncthreads();
+  if (lane == 0) red[warp] = rank;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int i = 0; i < 8; ++i) r += red[i];
+    atomicAdd(result + 0, (mx + logf(sum) - zl) * (2.f * T / Q));
+    if (r < 1.f) atomicAdd(result + 1, 100.f / Q);
+    if (r < 5.f) atomicAdd(result + 2, 100.f / Q);
+  }
+  const float inv = 1.f / sum, coef = 2.f / Q;
+  for (int c = threadIdx.x; c < Nk; c += 256) {
+    const float p = __expf(z[c] - mx) * inv;
+    z[c] = coef * (p - (c == label ? 1.f : 0.f));
+  }
+}
+
+// ---- masked-pixel MSE (E:85-111,141): target = un-normalised RGB patch '(p1 p2 c)' of view 0 at token row idx[r] -----
+// loss[0] += sum (pred - target)^2 / numel ; dpred = 2 (pred - target) / numel
+__global__ void __launch_bounds__(256)
+masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ images, const int* __restrict__ idx, float* __restrict__ loss,
+                  float* __restrict__ dpred, long long n_rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long numel = n_rows * 48;
+  float e = 0.f;
+  if (i < numel) {
+    const long long r = i / 48;
+    const int k = (int)(i % 48);
+    const int c = k % 3, p2 = (k / 3) & 3, p1 = k / 12;
+    const int tok_row = idx[r];
+    const long long b = tok_row >> 8;
+    const int tok = tok_row & 255, ph = tok >> 5, pw = tok & 31;
+    const float tgt = images[((b * 3 + c) * 32 + ph * 4 + p1) * 128 + pw * 4 + p2] * 0.5f + 0.5f;
+    const float df = pred[i] - tgt;
+    e = df * df;
+    if (dpred) dpred[i] = 2.f * df / (float)numel;
+  }
+  e = warp_sum(e);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(loss, t / (float)numel);
+  }
+}
+
+// y[i] = x[i] * s[0]  (apply an upstream scalar gradient that lives on the device)
+__global__ void scale_by_device_scalar_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * s[0];
+}
+
+}  // namespace dig
+
+using namespace dig;
+
+extern "C" int dig_l2norm_fwd(const float* x, float* y, float* inv_norm, int64_t rows, int32_t C, void* stream) {
+  DIG_REQUIRE(x && y && rows > 0 && C > 0, "dig_l2norm_fwd: bad arguments");
+  l2norm_fwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, y, inv_norm, rows, C);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, const float* gscale, float* dx, int64_t rows,
+                              int32_t C, void* stream) {
+  DIG_REQUIRE(dy && y && inv_norm && dx && rows > 0 && C > 0, "dig_l2norm_bwd: bad arguments");
+  l2norm_bwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dy, y, inv_norm, gscale, dx, rows, C);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_sgemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t b_is_nk, float alpha,
+                             void* stream) {
+  DIG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "dig_sgemm_f32: bad arguments");
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (b_is_nk) sgemm_f32_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, alpha);
+  else sgemm_f32_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, alpha);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_infonce_rows(float* logits, int32_t Q, int32_t Nk, int64_t label_offset, float T, float* result, void* stream) {
+  DIG_REQUIRE(logits && result && Q > 0 && Nk > 0, "dig_infonce_rows: bad arguments");
+  DIG_REQUIRE(label_offset >= 0 && label_offset + Q <= Nk, "dig_infonce_rows: labels [%lld, %lld) outside %d keys", (long long)label_offset,
+              (long long)label_offset + Q, Nk);
+  infonce_rows_kernel<<<Q, 256, 0, (cudaStream_t)stream>>>(logits, Q, Nk, label_offset, T, result);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_masked_mse(const float* pred, const float* images, const int32_t* idx, float* loss, float* dpred, int64_t n_rows,
+                              void* stream) {
+  DIG_REQUIRE(pred && images && idx && loss && n_rows > 0, "dig_masked_mse: bad arguments");
+  const long long numel = n_rows * 48;
+  masked_mse_kernel<<<(int)((numel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, images, idx, loss, dpred, n_rows);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_scale_by_device_scalar(const float* x, const float* s, float* y, int64_t n, void* stream) {
+  DIG_REQUIRE(x && s && y && n > 0, "dig_scale_by_device_scalar: bad arguments");
+  scale_by_device_scalar_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, s, y, n);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

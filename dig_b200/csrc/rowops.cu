@@ -1,0 +1,567 @@
+// dig_b200 -- HBM-bound row / column kernels of the pre-training step (coalesced, 64/128-bit vectorised).
+//   im2col for the 4x4 patch embed (F:188-195), LayerNorm forward/backward (F:134,140; M:424), window pooling
+//   (M:189-193), row gather / scatter-add for the masked-pixel decoder (M:563-570), column sums for bias
+//   gradients, BatchNorm1d batch statistics / apply / backward (M:463-482).
+#include "common.cuh"
+#include "../../include/dig_b200.h"
+
+namespace dig {
+
+// ------------------------------------------------------------------------------------------------
+// im2col: images fp32 [S,3,32,128] -> bf16 [S*256, 48]; column k = c*16 + kh*4 + kw (conv weight order)
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_patch4_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, c, kh): 4 kw values
+  if (idx >= total) return;
+  const int grp = (int)(idx % 12);
+  const long long row = idx / 12;
+  const int c = grp >> 2, kh = grp & 3;
+  const int tok = (int)(row & 255);
+  const long long s = row >> 8;
+  const int ph = tok >> 5, pw = tok & 31;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(img + ((s * 3 + c) * 32 + ph * 4 + kh) * 128 + pw * 4));
+  uint2 packed;
+  packed.x = pack_bf16(v.x, v.y);
+  packed.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(out + row * 48 + grp * 4) = packed;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, d <= 512, d % 64 == 0
+// ------------------------------------------------------------------------------------------------
+static constexpr int kLnMaxPairs = 8;  // float2 per lane
+
+template <bool GELU>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int d,
+                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int np = d >> 6;
+  const float* xr = x + row * d;
+  float2 v[kLnMaxPairs];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxPairs; ++k)
+    if (k < np) {
+      v[k] = *reinterpret_cast<const float2*>(xr + k * 64 + lane * 2);
+      s += v[k].x + v[k].y;
+    }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kLnMaxPairs; ++k)
+    if (k < np) {
+      const float a = v[k].x - mean, b = v[k].y - mean;
+      q += a * a + b * b;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+#pragma unroll
+  for (int k = 0; k < kLnMaxPairs; ++k)
+    if (k < np) {
+      const int c = k * 64 + lane * 2;
+      const float2 g = *reinterpret_cast<const float2*>(gamma + c);
+      const float2 b = *reinterpret_cast<const float2*>(beta + c);
+      float o0 = (v[k].x - mean) * rstd * g.x + b.x;
+      float o1 = (v[k].y - mean) * rstd * g.y + b.y;
+      if (GELU) { o0 = gelu_erf(o0); o1 = gelu_erf(o1); }
+      *reinterpret_cast<uint32_t*>(y + row * d + c) = pack_bf16(o0, o1);
+    }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// dx = dres + LN_bwd(dy);  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy  (dy is w.r.t. the LN (or GELU(LN)) output)
+template <bool GELU>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* dres, float* dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int d) {
+  extern __shared__ float part[];  // [2][d] block partials
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int np = d >> 6;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  float2 ag[kLnMaxPairs], ab[kLnMaxPairs];
+#pragma unroll
+  for (int k = 0; k < kLnMaxPairs; ++k) { ag[k] = make_float2(0.f, 0.f); ab[k] = make_float2(0.f, 0.f); }
+  float2 gm[kLnMaxPairs], bt[kLnMaxPairs];
+#pragma unroll
+  for (int k = 0; k < kLnMaxPairs; ++k)
+    if (k < np) {
+      gm[k] = *reinterpret_cast<const float2*>(gamma + k * 64 + lane * 2);
+      bt[k] = GELU ? *reinterpret_cast<const float2*>(beta + k * 64 + lane * 2) : make_float2(0.f, 0.f);
+    }
+  for (long long row = (long long)blockIdx.x * nwarps + warp; row < rows; row += (long long)gridDim.x * nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float2 xh[kLnMaxPairs], g[kLnMaxPairs];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxPairs; ++k)
+      if (k < np) {
+        const int c = k * 64 + lane * 2;
+        const float2 xv = *reinterpret_cast<const float2*>(x + row * d + c);
+        const uint32_t dv = *reinterpret_cast<const uint32_t*>(dy + row * d + c);
+        xh[k] = make_float2((xv.x - mu) * rs, (xv.y - mu) * rs);
+        float d0 = bf16_lo(dv), d1 = bf16_hi(dv);
+        if (GELU) {
+          d0 *= gelu_erf_grad(xh[k].x * gm[k].x + bt[k].x);
+          d1 *= gelu_erf_grad(xh[k].y * gm[k].y + bt[k].y);
+        }
+        ag[k].x += d0 * xh[k].x; ag[k].y += d1 * xh[k].y;
+        ab[k].x += d0; ab[k].y += d1;
+        g[k] = make_float2(d0 * gm[k].x, d1 * gm[k].y);
+        c1 += g[k].x + g[k].y;
+        c2 += g[k].x * xh[k].x + g[k].y * xh[k].y;
+      }
+    c1 = warp_sum(c1) / d;
+    c2 = warp_sum(c2) / d;
+#pragma unroll
+    for (int k = 0; k < kLnMaxPairs; ++k)
+      if (k < np) {
+        const int c = k * 64 + lane * 2;
+        float o0 = rs * (g[k].x - c1 - xh[k].x * c2);
+        float o1 = rs * (g[k].y - c1 - xh[k].y * c2);
+        if (dres) {
+          const float2 r = *reinterpret_cast<const float2*>(dres + row * d + c);
+          o0 += r.x; o1 += r.y;
+        }
+        if (dx_f32) *reinterpret_cast<float2*>(dx_f32 + row * d + c) = make_float2(o0, o1);
+        if (dx_bf16) *reinterpret_cast<uint32_t*>(dx_bf16 + row * d + c) = pack_bf16(o0, o1);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < kLnMaxPairs; ++k)
+    if (k < np) {
+      const int c = k * 64 + lane * 2;
+      atomicAdd(&part[c], ag[k].x); atomicAdd(&part[c + 1], ag[k].y);
+      atomicAdd(&part[d + c], ab[k].x); atomicAdd(&part[d + c + 1], ab[k].y);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(dgamma + i, part[i]);
+    atomicAdd(dbeta + i, part[d + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// window pooling (PatchNet without patch transformer): [S,8,32,d] -> mean over 8 rows x 8 columns -> [S,4,d]
+// sequences [0, split) are read from x0, the rest from x1 (masked view after pix_projector | augmented view)
+// ------------------------------------------------------------------------------------------------
+__global__ void pool_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ x1, long long split, __nv_bfloat16* __restrict__ out,
+                                long long num_seqs, int d, int num_windows) {
+  const int dv = d >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_seqs * num_windows * dv) return;
+  const int c4 = (int)(idx % dv);
+  const int w = (int)((idx / dv) % num_windows);
+  const long long s = idx / ((long long)dv * num_windows);
+  const float* src = (s < split) ? (x0 + s * 256 * d) : (x1 + (s - split) * 256 * d);
+  const int wcols = 32 / num_windows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int h = 0; h < 8; ++h)
+    for (int cc = 0; cc < wcols; ++cc) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)(h * 32 + w * wcols + cc) * d + c4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  const float inv = 1.0f / (8 * wcols);
+  uint2 p;
+  p.x = pack_bf16(acc.x * inv, acc.y * inv);
+  p.y = pack_bf16(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(out + (s * num_windows + w) * d + c4 * 4) = p;
+}
+
+// dx[s, tok, :] = dpool[s, window(tok), :] / window_size, written to dx0 (s < split) or dx1
+__global__ void pool_bwd_kernel(const float* __restrict__ dpool, long long split, float* __restrict__ dx0, float* __restrict__ dx1,
+                                long long num_seqs, int d, int num_windows) {
+  const int dv = d >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_seqs * 256 * dv) return;
+  const int c4 = (int)(idx % dv);
+  const int tok = (int)((idx / dv) & 255);
+  const long long s = idx / ((long long)dv * 256);
+  const int wcols = 32 / num_windows;
+  const int w = (tok & 31) / wcols;
+  const float inv = 1.0f / (8 * wcols);
+  float4 v = *reinterpret_cast<const float4*>(dpool + (s * num_windows + w) * d + c4 * 4);
+  v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+  float* dst = (s < split) ? (dx0 + (s * 256 + tok) * d) : (dx1 + ((s - split) * 256 + tok) * d);
+  *reinterpret_cast<float4*>(dst + c4 * 4) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row gather (fp32 -> bf16) and scatter-add (fp32 += fp32) by int32 row index
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, __nv_bfloat16* __restrict__ out, long long n,
+                                   int d) {
+  const int dv = d >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dv) return;
+  const long long r = i / dv;
+  const int c4 = (int)(i % dv);
+  const float4 v = *reinterpret_cast<const float4*>(x + (long long)idx[r] * d + c4 * 4);
+  uint2 p;
+  p.x = pack_bf16(v.x, v.y);
+  p.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(out + r * d + c4 * 4) = p;
+}
+
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ dst, long long n,
+                                        int d) {
+  const int dv = d >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dv) return;
+  const long long r = i / dv;
+  const int c4 = (int)(i % dv);
+  const float4 v = *reinterpret_cast<const float4*>(src + r * d + c4 * 4);
+  float4* o = reinterpret_cast<float4*>(dst + (long long)idx[r] * d + c4 * 4);
+  float4 t = *o;
+  t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+  *o = t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums: out[n] += sum_m x[m, n]   (bias gradients).  Block = 32 column lanes x 8 row lanes.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T, bool SQUARES>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, float* __restrict__ out_sq, long long rows, int cols,
+              int rows_per_block) {
+  __shared__ float sm[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f, q = 0.f;
+  if (col < cols)
+    for (long long r = r0 + ry; r < r1; r += 8) {
+      const float v = ld_as_float<T>(x + r * ld + col);
+      s += v;
+      if (SQUARES) q += v * v;
+    }
+  sm[0][ry][cx] = s;
+  sm[1][ry][cx] = q;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ts += sm[0][k][cx]; tq += sm[1][k][cx]; }
+    atomicAdd(out + col, ts);
+    if (SQUARES) atomicAdd(out_sq + col, tq);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d (training mode).  stats = [sum(C) | sumsq(C)] over `count` rows (possibly all-reduced across ranks).
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int relu, float eps, __nv_bfloat16* __restrict__ y_bf16,
+                                float* __restrict__ y_f32, long long rows, int C) {
+  const int cv = C >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cv) return;
+  const int c = (int)(i % cv) * 4;
+  const long long r = i / cv;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
+  const float4 s = *reinterpret_cast<const float4*>(stats + c);
+  const float4 q = *reinterpret_cast<const float4*>(stats + C + c);
+  const float inv = 1.0f / count;
+  float o[4];
+  const float xv[4] = {v.x, v.y, v.z, v.w}, sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float mu = sv[k] * inv;
+    const float var = fmaxf(qv[k] * inv - mu * mu, 0.f);
+    float t = (xv[k] - mu) * rsqrtf(var + eps);
+    if (gamma) t = t * gamma[c + k] + beta[c + k];
+    if (relu) t = fmaxf(t, 0.f);
+    o[k] = t;
+  }
+  if (y_bf16) {
+    uint2 p;
+    p.x = pack_bf16(o[0], o[1]);
+    p.y = pack_bf16(o[2], o[3]);
+    *reinterpret_cast<uint2*>(y_bf16 + r * C + c) = p;
+  }
+  if (y_f32) *reinterpret_cast<float4*>(y_f32 + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// running_mean/var update (momentum 0.1, unbiased variance), num_batches_tracked += 1
+__global__ void bn_running_kernel(const float* __restrict__ stats, float count, float momentum, float* __restrict__ running_mean,
+                                  float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float mu = stats[c] / count;
+    const float var = fmaxf(stats[C + c] / count - mu * mu, 0.f);
+    const float unbiased = var * (count / fmaxf(count - 1.f, 1.f));
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+}
+
+// backward statistics: bstats = [sum dy | sum dy*xhat]  (dy already masked by the ReLU of this layer)
+__global__ void __launch_bounds__(256)
+bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats, float count, float eps,
+                    float* __restrict__ bstats, long long rows, int C, int rows_per_block) {
+  __shared__ float sm[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f, q = 0.f;
+  if (col < C) {
+    const float mu = stats[col] / count;
+    const float rs = rsqrtf(fmaxf(stats[C + col] / count - mu * mu, 0.f) + eps);
+    for (long long r = r0 + ry; r < r1; r += 8) {
+      const float g = dy[r * C + col];
+      s += g;
+      q += g * (x[r * C + col] - mu) * rs;
+    }
+  }
+  sm[0][ry][cx] = s;
+  sm[1][ry][cx] = q;
+  __syncthreads();
+  if (ry == 0 && col < C) {
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ts += sm[0][k][cx]; tq += sm[1][k][cx]; }
+    atomicAdd(bstats + col, ts);
+    atomicAdd(bstats + C + col, tq);
+  }
+}
+
+// dx = gamma * rstd * (dy - sum_dy/n - xhat * sum_dy_xhat/n)   (bstats/count possibly all-reduced across ranks)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                                    const float* __restrict__ bstats, float count, const float* __restrict__ gamma, float eps,
+                                    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dx_f32, long long rows, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int c = (int)(i % C);
+  const float mu = stats[c] / count;
+  const float rs = rsqrtf(fmaxf(stats[C + c] / count - mu * mu, 0.f) + eps);
+  const float xh = (x[i] - mu) * rs;
+  const float g = gamma ? gamma[c] : 1.f;
+  const float v = g * rs * (dy[i] - bstats[c] / count - xh * bstats[C + c] / count);
+  if (dx_bf16) dx_bf16[i] = __float2bfloat16(v);
+  if (dx_f32) dx_f32[i] = v;
+}
+
+// fp32 -> bf16 elementwise
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  uint2 p;
+  p.x = pack_bf16(v.x, v.y);
+  p.y = pack_bf16(v.z, v.w);
+  reinterpret_cast<uint2*>(y)[i] = p;
+}
+
+// y (bf16) = row_mask[r] ? 0 : x  (gradient reaching the patch-embed GEMM: masked tokens were replaced by mask_token, V:95-97)
+__global__ void zero_masked_rows_kernel(const float* __restrict__ x, const uint8_t* __restrict__ row_mask, __nv_bfloat16* __restrict__ y,
+                                        long long rows, int d) {
+  const int dv = d >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * dv) return;
+  const long long r = i / dv;
+  float4 v = reinterpret_cast<const float4*>(x)[i];
+  if (row_mask[r]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint2 p;
+  p.x = pack_bf16(v.x, v.y);
+  p.y = pack_bf16(v.z, v.w);
+  reinterpret_cast<uint2*>(y)[i] = p;
+}
+
+// mask u8 [B,256] -> idx[b*n_per + j] = b*256 + position of the j-th set bit (boolean-mask order, M:569); one warp per sample.
+// err[0] is set when a sample does not have exactly n_per set bits.
+__global__ void mask_to_index_kernel(const uint8_t* __restrict__ mask, int* __restrict__ idx, int* __restrict__ err, int B, int n_per) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int base = 0;
+  for (int t0 = 0; t0 < 256; t0 += 32) {
+    const int set = mask[(long long)b * 256 + t0 + lane] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, set);
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    if (set && pos < n_per) idx[(long long)b * n_per + pos] = b * 256 + t0 + lane;
+    base += __popc(bal);
+  }
+  if (lane == 0 && base != n_per) atomicExch(err, 1);
+}
+
+static inline int blocks_for(long long n, int per) { return (int)((n + per - 1) / per); }
+
+}  // namespace dig
+
+using namespace dig;
+
+extern "C" int dig_im2col_patch4(const float* images, void* out, int64_t num_images, void* stream) {
+  DIG_REQUIRE(images && out && num_images > 0, "dig_im2col_patch4: bad arguments");
+  const long long total = (long long)num_images * 256 * 12;
+  im2col_patch4_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(images, (__nv_bfloat16*)out, total);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows,
+                                 int32_t d, float eps, int32_t gelu, void* stream) {
+  DIG_REQUIRE(x && gamma && beta && y && rows > 0, "dig_layernorm_fwd: bad arguments");
+  DIG_REQUIRE(d % 64 == 0 && d <= 512, "dig_layernorm_fwd: d must be a multiple of 64 and <= 512 (got %d)", d);
+  const int grid = blocks_for(rows, 8);
+  if (gelu) layernorm_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, d, eps);
+  else layernorm_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, d, eps);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                                 int64_t rows, int32_t d, int32_t gelu, void* stream) {
+  DIG_REQUIRE(dy && x && mean && rstd && gamma && dgamma && dbeta && rows > 0, "dig_layernorm_bwd: bad arguments");
+  DIG_REQUIRE(d % 64 == 0 && d <= 512, "dig_layernorm_bwd: d must be a multiple of 64 and <= 512 (got %d)", d);
+  DIG_REQUIRE(!gelu || beta, "dig_layernorm_bwd: gelu variant needs beta");
+  int grid = num_sms() * 4;
+  if (grid > blocks_for(rows, 8)) grid = blocks_for(rows, 8);
+  const size_t sm = 2 * d * sizeof(float);
+  if (gelu)
+    layernorm_bwd_kernel<true><<<grid, 256, sm, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, x, mean, rstd, gamma, beta, dres, dx_f32,
+                                                                      (__nv_bfloat16*)dx_bf16, dgamma, dbeta, rows, d);
+  else
+    layernorm_bwd_kernel<false><<<grid, 256, sm, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, x, mean, rstd, gamma, beta, dres, dx_f32,
+                                                                       (__nv_bfloat16*)dx_bf16, dgamma, dbeta, rows, d);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_pool_fwd(const float* x0, const float* x1, int64_t split, void* out, int64_t num_seqs, int32_t d, int32_t num_windows,
+                            void* stream) {
+  DIG_REQUIRE(x0 && out && num_seqs > 0 && d % 4 == 0, "dig_pool_fwd: bad arguments");
+  DIG_REQUIRE(num_windows > 0 && 32 % num_windows == 0, "dig_pool_fwd: num_windows must divide 32 (got %d)", num_windows);
+  DIG_REQUIRE(split >= num_seqs || x1, "dig_pool_fwd: x1 missing");
+  const long long total = (long long)num_seqs * num_windows * (d / 4);
+  pool_fwd_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x0, x1, split, (__nv_bfloat16*)out, num_seqs, d, num_windows);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_pool_bwd(const float* dpool, int64_t split, float* dx0, float* dx1, int64_t num_seqs, int32_t d, int32_t num_windows,
+                            void* stream) {
+  DIG_REQUIRE(dpool && dx0 && num_seqs > 0 && d % 4 == 0, "dig_pool_bwd: bad arguments");
+  DIG_REQUIRE(num_windows > 0 && 32 % num_windows == 0, "dig_pool_bwd: num_windows must divide 32 (got %d)", num_windows);
+  const long long total = (long long)num_seqs * 256 * (d / 4);
+  pool_bwd_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dpool, split, dx0, dx1, num_seqs, d, num_windows);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_gather_rows(const float* x, const int32_t* idx, void* out, int64_t n, int32_t d, void* stream) {
+  DIG_REQUIRE(x && idx && out && d % 4 == 0, "dig_gather_rows: bad arguments");
+  if (n == 0) return 0;
+  gather_rows_kernel<<<blocks_for(n * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, idx, (__nv_bfloat16*)out, n, d);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_scatter_add_rows(const float* src, const int32_t* idx, float* dst, int64_t n, int32_t d, void* stream) {
+  DIG_REQUIRE(src && idx && dst && d % 4 == 0, "dig_scatter_add_rows: bad arguments");
+  if (n == 0) return 0;
+  scatter_add_rows_kernel<<<blocks_for(n * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, idx, dst, n, d);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_colsum(const void* x, int32_t x_is_fp32, int64_t ld, float* out, float* out_sq, int64_t rows, int32_t cols,
+                          void* stream) {
+  DIG_REQUIRE(x && out && rows > 0 && cols > 0, "dig_colsum: bad arguments");
+  const int gx = (cols + 31) / 32;
+  int gy = (num_sms() * 8 + gx - 1) / gx;
+  if (gy > (rows + 63) / 64) gy = (int)((rows + 63) / 64);
+  if (gy < 1) gy = 1;
+  const int rpb = (int)((rows + gy - 1) / gy);
+  dim3 grid(gx, gy);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_is_fp32) {
+    if (out_sq) colsum_kernel<float, true><<<grid, 256, 0, s>>>((const float*)x, ld, out, out_sq, rows, cols, rpb);
+    else colsum_kernel<float, false><<<grid, 256, 0, s>>>((const float*)x, ld, out, nullptr, rows, cols, rpb);
+  } else {
+    if (out_sq) colsum_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, out_sq, rows, cols, rpb);
+    else colsum_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, nullptr, rows, cols, rpb);
+  }
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_bn_apply(const float* x, const float* stats, float count, const float* gamma, const float* beta, int32_t relu, float eps,
+                            void* y_bf16, float* y_f32, int64_t rows, int32_t C, void* stream) {
+  DIG_REQUIRE(x && stats && rows > 0 && C % 4 == 0 && count > 0, "dig_bn_apply: bad arguments");
+  DIG_REQUIRE((gamma == nullptr) == (beta == nullptr), "dig_bn_apply: gamma and beta must both be given or both be NULL");
+  bn_apply_kernel<<<blocks_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, stats, count, gamma, beta, relu, eps,
+                                                                                   (__nv_bfloat16*)y_bf16, y_f32, rows, C);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_bn_running(const float* stats, float count, float momentum, float* running_mean, float* running_var,
+                              int64_t* num_batches_tracked, int32_t C, void* stream) {
+  DIG_REQUIRE(stats && running_mean && running_var && C > 0 && count > 0, "dig_bn_running: bad arguments");
+  bn_running_kernel<<<blocks_for(C, 256), 256, 0, (cudaStream_t)stream>>>(stats, count, momentum, running_mean, running_var,
+                                                                        (long long*)num_batches_tracked, C);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_bn_bwd_stats(const float* dy, const float* x, const float* stats, float count, float eps, float* bstats, int64_t rows,
+                                int32_t C, void* stream) {
+  DIG_REQUIRE(dy && x && stats && bstats && rows > 0 && C > 0 && count > 0, "dig_bn_bwd_stats: bad arguments");
+  const int gx = (C + 31) / 32;
+  int gy = (num_sms() * 8 + gx - 1) / gx;
+  if (gy > (rows + 63) / 64) gy = (int)((rows + 63) / 64);
+  if (gy < 1) gy = 1;
+  const int rpb = (int)((rows + gy - 1) / gy);
+  bn_bwd_stats_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, count, eps, bstats, rows, C, rpb);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_bn_bwd_apply(const float* dy, const float* x, const float* stats, const float* bstats, float count, const float* gamma,
+                                float eps, void* dx_bf16, float* dx_f32, int64_t rows, int32_t C, void* stream) {
+  DIG_REQUIRE(dy && x && stats && bstats && rows > 0 && C > 0 && count > 0, "dig_bn_bwd_apply: bad arguments");
+  bn_bwd_apply_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, bstats, count, gamma, eps,
+                                                                                 (__nv_bfloat16*)dx_bf16, dx_f32, rows, C);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  DIG_REQUIRE(x && y && n > 0 && n % 4 == 0, "dig_cast_f32_bf16: n must be a positive multiple of 4");
+  cast_f32_bf16_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n / 4);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_zero_masked_rows(const float* x, const uint8_t* row_mask, void* y, int64_t rows, int32_t d, void* stream) {
+  DIG_REQUIRE(x && row_mask && y && rows > 0 && d % 4 == 0, "dig_zero_masked_rows: bad arguments");
+  zero_masked_rows_kernel<<<blocks_for(rows * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, row_mask, (__nv_bfloat16*)y, rows, d);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_mask_to_index(const uint8_t* mask, int32_t* idx, int32_t* err, int32_t B, int32_t n_per, void* stream) {
+  DIG_REQUIRE(mask && idx && err && B > 0 && n_per >= 0 && n_per <= 256, "dig_mask_to_index: bad arguments");
+  mask_to_index_kernel<<<blocks_for(B, 8), 256, 0, (cudaStream_t)stream>>>(mask, idx, err, B, n_per);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

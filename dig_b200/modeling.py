@@ -207,7 +207,8 @@ class DigMoCoViT(nn.Module):
         """Same contract as M:488-577: returns {'contra_loss', 'q{1,2}_acc{1,5}', 'vis_out': [ [B,n,48] ]}."""
         if not image.is_cuda:
             raise RuntimeError("dig_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
-        return self._pipeline().forward(image, aug_image, vis_mask_pos, float(m), bool(only_mim_on_ori_img))
+        from .pretrain_step import run_model
+        return run_model(self._pipeline(), image, aug_image, vis_mask_pos, float(m), bool(only_mim_on_ori_img))
 
 
 def _factory(embed_dim, heads, **kwargs):

@@ -41,6 +41,33 @@ class _Gemm(ctypes.Structure):
 EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_RELU_MASK = 0, 1, 2, 3
 
 
+_CTYPE = {"int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "float": ctypes.c_float, "int": ctypes.c_int}
+
+
+def header_path():
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dig_b200.h")
+
+
+def parse_header(path=None):
+    """{function name: [ctypes argument types]} for every `int dig_*(...)` declared in include/dig_b200.h."""
+    import re
+    text = open(path or header_path()).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(int|const char\*)\s+(dig_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        argtypes = []
+        if args not in ("", "void"):
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    argtypes.append(_CTYPE[a.replace("const ", "").split()[0]])
+        decls[name] = (ret, argtypes)
+    return decls
+
+
 def load():
     """Load the in-tree shared library; raises DigError when it has not been built."""
     global _lib
@@ -51,15 +78,21 @@ def load():
         raise DigError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(dig_b200 has no CPU / eager fallback)" % path)
     lib = ctypes.CDLL(path)
-    lib.dig_last_error.restype = ctypes.c_char_p
-    lib.dig_version.restype = ctypes.c_int
-    lib.dig_sm.restype = ctypes.c_int
-    lib.dig_gemm.argtypes = [ctypes.POINTER(_Gemm), ctypes.c_void_p]
-    vp, i64, i32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
-    lib.dig_attention_fwd.argtypes = [vp, vp, vp, i64, i32, f32, i32, vp]
-    lib.dig_attention_bwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, vp]
+    for name, (ret, argtypes) in parse_header().items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = ctypes.c_char_p if ret != "int" else ctypes.c_int
+        fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def call(name, *args):
+    """Generic C-ABI call: torch tensors are passed by data_ptr(), None as NULL; the current stream is appended."""
+    lib = load()
+    conv = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
+    rc = getattr(lib, name)(*conv, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise DigError("%s failed (%d): %s" % (name, rc, lib.dig_last_error().decode()))
 
 
 def _check(rc, what):

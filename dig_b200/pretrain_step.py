@@ -1,0 +1,552 @@
+"""Sequencing of DiG's pre-training forward/backward on the sm_100a kernels (boundary B1 -> B3).
+
+`PretrainStep.forward` reproduces `MoCo_ViT.forward` (reference modeling_pretrain_moco_mim_ori.py:488-577, tag M)
+and `PretrainStep.backward` its autograd, but every arithmetic step is a C-ABI call into libdig_b200.so
+(dig_b200/ops.py).  torch is used for what the brief allows: owning device buffers, the current stream,
+autograd plumbing (one custom Function for the whole model) and torch.distributed collectives (MoCo key
+all_gather M:580-591, SyncBatchNorm statistics R:390).
+
+Activation layout in HBM (tokens = 2B sequences x 256 patch tokens, view-major: rows [0, B*256) are the masked
+view, rows [B*256, 2B*256) the augmented view, exactly torch.cat([image, aug_image]) of M:491):
+  * residual stream           fp32 [tokens, d]     one buffer per half-block (kept for the backward)
+  * GEMM operands             bf16 [tokens, d|3d|4d] (LayerNorm outputs, qkv, attention context, GELU in/out)
+  * weights                   fp32 master nn.Parameters + bf16 shadows refreshed once per step
+  * head activations          fp32 pre-BatchNorm, bf16 post-BatchNorm (GEMM operands)
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .ops import call
+
+F32, BF16 = torch.float32, torch.bfloat16
+TOK = 256
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+class MtTable:
+    """Device-side pointer table for the multi-tensor kernels (dig_b200/csrc/optim.cu)."""
+
+    def __init__(self, device, *tensor_lists):
+        n = len(tensor_lists[0])
+        chunk = ops.load().dig_mt_chunk()
+        self.keep = tensor_lists
+        self.ptrs = [torch.tensor([0 if t is None else t.data_ptr() for t in lst], dtype=torch.int64, device=device)
+                     for lst in tensor_lists]
+        numel = [tensor_lists[0][i].numel() for i in range(n)]
+        self.numel = torch.tensor(numel, dtype=torch.int64, device=device)
+        bt, bc = [], []
+        for i, ne in enumerate(numel):
+            for c in range((ne + chunk - 1) // chunk):
+                bt.append(i)
+                bc.append(c)
+        self.blk_tensor = torch.tensor(bt, dtype=torch.int32, device=device)
+        self.blk_chunk = torch.tensor(bc, dtype=torch.int32, device=device)
+        self.num_blocks = len(bt)
+        self.signature = tuple(0 if t is None else t.data_ptr() for lst in tensor_lists for t in lst)
+
+
+class _Bufs:
+    """Named, shape-checked device buffers (allocated once per batch size)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.d = {}
+
+    def get(self, name, shape, dtype):
+        t = self.d.get(name)
+        shape = tuple(int(s) for s in shape)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.d[name] = t
+        return t
+
+
+def _split_k(m, n, k, bn=128):
+    tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+    kb = (k + 63) // 64
+    return max(1, min(kb, 148 // max(tiles, 1)))
+
+
+class PretrainStep:
+    GEMM_WEIGHTS_BLOCK = ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")
+
+    def __init__(self, model):
+        ops.load()
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise ops.DigError("dig_b200 runs on sm_100a only: move the model to a CUDA device first")
+        self.model = model
+        self.device = p0.device
+        enc = model.encoder
+        self.d = enc.embed_dim
+        self.heads = enc.num_heads
+        if self.d != self.heads * 64:
+            raise ops.DigError("head_dim must be 64 (d=%d heads=%d)" % (self.d, self.heads))
+        self.depth = len(enc.blocks)
+        self.T = float(model.T)
+        self.num_windows = int(model.num_windows)
+        self.scale = 64 ** -0.5
+        self.bufs = _Bufs(self.device)
+        self.pos = enc.pos_embed.reshape(TOK, self.d).to(self.device, F32).contiguous()
+        self._named = dict(model.named_parameters())
+        self._ptr_sig = self._signature()
+        self._build_shadows()
+        self.saved = None
+        self._n_masked = {}
+
+    # ------------------------------------------------------------------ parameter bookkeeping
+    def _signature(self):
+        return tuple(p.data_ptr() for p in self._named.values())
+
+    def matches(self, model):
+        return model is self.model and self._signature() == self._ptr_sig
+
+    def _gemm_weight_names(self, prefix_enc, prefix_proj, prefix_pix, predictor):
+        names = [prefix_enc + "patch_embed.proj.weight"]
+        for l in range(self.depth):
+            names += ["%sblocks.%d.%s" % (prefix_enc, l, w) for w in self.GEMM_WEIGHTS_BLOCK]
+        names += ["%s%d.weight" % (prefix_proj, i) for i in (0, 3, 6)]
+        names += ["%s%d.weight" % (prefix_pix, i) for i in (0, 3, 6)]
+        if predictor:
+            names += ["predictor.0.weight", "predictor.3.weight", "pix_decoder.0.weight", "pix_decoder.1.weight",
+                      "pix_decoder.4.weight"]
+        return names
+
+    def _build_shadows(self):
+        """bf16 shadows of every GEMM weight (online + momentum), views into one flat buffer (16-byte aligned)."""
+        on = self._gemm_weight_names("encoder.", "encoder_projection_layer.", "pix_projector.", True)
+        mo = self._gemm_weight_names("momentum_encoder.", "momentum_projection_layer.", "pix_projector_m.", False)
+        total = 0
+        offs = {}
+        for n in on + mo:
+            offs[n] = total
+            total += (self._named[n].numel() + 7) // 8 * 8
+        flat = torch.zeros(total, dtype=BF16, device=self.device)
+        self.shadow = {}
+        for n in on + mo:
+            p = self._named[n]
+            shape = (p.shape[0], p.numel() // p.shape[0])
+            self.shadow[n] = flat[offs[n]:offs[n] + p.numel()].view(shape)
+        self.shadow_flat = flat
+        self.tab_cast_online = MtTable(self.device, [self._named[n].data for n in on], [self.shadow[n] for n in on])
+        self.tab_cast_momentum = MtTable(self.device, [self._named[n].data for n in mo], [self.shadow[n] for n in mo])
+        # EMA pairs: every parameter of encoder / projector / pix_projector (M:428-442)
+        pairs = []
+        for src, dst in (("encoder.", "momentum_encoder."), ("encoder_projection_layer.", "momentum_projection_layer."),
+                         ("pix_projector.", "pix_projector_m.")):
+            for n, p in self._named.items():
+                if n.startswith(src):
+                    pairs.append((p.data, self._named[dst + n[len(src):]].data, self.shadow.get(dst + n[len(src):])))
+        self.tab_ema = MtTable(self.device, [a for a, _, _ in pairs], [b for _, b, _ in pairs], [c for _, _, c in pairs])
+        # fused qkv bias [q_bias | 0 | v_bias] per block (F:91) for both encoders
+        d, L = self.d, self.depth
+        self.qkv_bias = {"encoder.": torch.zeros(L, 3 * d, device=self.device), "momentum_encoder.": torch.zeros(L, 3 * d, device=self.device)}
+        src, dst = [], []
+        for pre in ("encoder.", "momentum_encoder."):
+            for l in range(L):
+                src += [self._named["%sblocks.%d.attn.q_bias" % (pre, l)].data, self._named["%sblocks.%d.attn.v_bias" % (pre, l)].data]
+                dst += [self.qkv_bias[pre][l, :d], self.qkv_bias[pre][l, 2 * d:]]
+        self.tab_qkv_bias = MtTable(self.device, src, dst)
+        # trainable parameters, in named_parameters order, and their flat gradient buffer
+        self.train_names = [n for n, p in self._named.items() if p.requires_grad]
+        goff, total = {}, 0
+        for n in self.train_names:
+            goff[n] = total
+            total += (self._named[n].numel() + 3) // 4 * 4
+        self.grad_off, self.grad_total = goff, total
+        self.momentum_warm = False
+
+    def trainable_params(self):
+        return [self._named[n] for n in self.train_names]
+
+    def _grad_views(self, flat):
+        out = {}
+        for n in self.train_names:
+            p = self._named[n]
+            out[n] = flat[self.grad_off[n]:self.grad_off[n] + p.numel()].view(p.shape)
+        return out
+
+    # ------------------------------------------------------------------ small helpers
+    def _mt(self, fn, tab, *extra):
+        lib = ops.load()
+        rc = getattr(lib, fn)(*[t.data_ptr() for t in tab.ptrs], tab.numel.data_ptr(), tab.blk_tensor.data_ptr(),
+                              tab.blk_chunk.data_ptr(), tab.num_blocks, *extra, torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise ops.DigError("%s failed: %s" % (fn, lib.dig_last_error().decode()))
+
+    def _bn_sync(self, bn):
+        w, _ = _world()
+        return w > 1 and isinstance(bn, torch.nn.SyncBatchNorm)
+
+    def _ln(self, x, w, b, y, mean, rstd, gelu=0, eps=1e-6):
+        call("dig_layernorm_fwd", x, w, b, y, mean, rstd, x.shape[0], x.shape[1], eps, gelu)
+
+    # ------------------------------------------------------------------ encoder
+    def _enc_weights(self, pre):
+        N, S = self._named, self.shadow
+        blocks = []
+        for l in range(self.depth):
+            b = "%sblocks.%d." % (pre, l)
+            blocks.append(dict(n1w=N[b + "norm1.weight"], n1b=N[b + "norm1.bias"], qkvw=S[b + "attn.qkv.weight"],
+                               qkvb=self.qkv_bias[pre][l], pw=S[b + "attn.proj.weight"], pb=N[b + "attn.proj.bias"],
+                               n2w=N[b + "norm2.weight"], n2b=N[b + "norm2.bias"], f1w=S[b + "mlp.fc1.weight"],
+                               f1b=N[b + "mlp.fc1.bias"], f2w=S[b + "mlp.fc2.weight"], f2b=N[b + "mlp.fc2.bias"], name=b))
+        return dict(pew=S[pre + "patch_embed.proj.weight"], peb=N[pre + "patch_embed.proj.bias"],
+                    mtok=N[pre + "mask_token"].reshape(-1), blocks=blocks, pre=pre)
+
+    def _encoder_fwd(self, W, images, mask_u8, tag, save):
+        """V:89-106. images fp32 [S,3,32,128]; mask_u8 [S*256]. Returns fp32 [S*256, d]; saves activations when `save`."""
+        B = self.bufs
+        S = images.shape[0]
+        M, d, h = S * TOK, self.d, self.heads
+        a0 = B.get(tag + "a0", (M, 48), BF16)
+        call("dig_im2col_patch4", images, a0, S)
+        x = B.get(tag + "x0", (M, d), F32)
+        ops.gemm(a0, W["pew"], x, bias=W["peb"], residual=self.pos, res_row_mod=TOK, row_mask=mask_u8, row_mask_value=W["mtok"])
+        acts = []
+        for l, bw in enumerate(W["blocks"]):
+            t = (tag + "b%d." % l) if save else (tag + "b.")
+            ln1 = B.get(t + "ln1", (M, d), BF16)
+            mean1, rstd1 = B.get(t + "m1", (M,), F32), B.get(t + "r1", (M,), F32)
+            self._ln(x, bw["n1w"], bw["n1b"], ln1, mean1, rstd1)
+            qkv = B.get(t + "qkv", (M, 3 * d), BF16)
+            ops.gemm(ln1, bw["qkvw"], qkv, bias=bw["qkvb"])
+            att = B.get(t + "att", (M, d), BF16)
+            lse = B.get(t + "lse", (S, h, TOK), F32)
+            ops.attention_fwd(qkv, att, lse, h, self.scale)
+            xm = B.get(t + "xm" if save else tag + "xm", (M, d), F32)
+            ops.gemm(att, bw["pw"], xm, bias=bw["pb"], residual=x)
+            ln2 = B.get(t + "ln2", (M, d), BF16)
+            mean2, rstd2 = B.get(t + "m2", (M,), F32), B.get(t + "r2", (M,), F32)
+            self._ln(xm, bw["n2w"], bw["n2b"], ln2, mean2, rstd2)
+            hpre = B.get(t + "hpre", (M, 4 * d), BF16)
+            hpost = B.get(t + "hpost", (M, 4 * d), BF16)
+            ops.gemm(ln2, bw["f1w"], hpost, bias=bw["f1b"], epilogue=ops.EPI_GELU, aux=hpre)
+            xn = B.get((tag + "x%d" % (l + 1)) if save else (tag + "x%d" % ((l + 1) % 2 + 1)), (M, d), F32)
+            ops.gemm(hpost, bw["f2w"], xn, bias=bw["f2b"], residual=xm)
+            if save:
+                acts.append(dict(x=x, ln1=ln1, mean1=mean1, rstd1=rstd1, qkv=qkv, att=att, lse=lse, xm=xm, ln2=ln2, mean2=mean2,
+                                 rstd2=rstd2, hpre=hpre, hpost=hpost))
+            x = xn
+        return x, dict(a0=a0, acts=acts, mask=mask_u8)
+
+    def _encoder_bwd(self, W, sv, g, gb, grads):
+        """g fp32 / gb bf16 [M,d]: gradient w.r.t. the encoder output.  Accumulates parameter gradients into `grads`."""
+        B = self.bufs
+        M, d, h = g.shape[0], self.d, self.heads
+        S = M // TOK
+        dh = B.get("bw.dh", (M, 4 * d), BF16)
+        dln = B.get("bw.dln", (M, d), BF16)
+        dat = B.get("bw.dat", (M, d), BF16)
+        dqkv = B.get("bw.dqkv", (M, 3 * d), BF16)
+        dqkvb = B.get("bw.dqkvb", (3 * d,), F32)
+        for l in reversed(range(self.depth)):
+            bw, a = W["blocks"][l], sv["acts"][l]
+            nm = bw["name"]
+            # ---- MLP (F:53-60) ----
+            call("dig_colsum", gb, 0, d, grads[nm + "mlp.fc2.bias"], None, M, d)
+            ops.gemm(gb, a["hpost"], grads[nm + "mlp.fc2.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(d, 4 * d, M))
+            ops.gemm(gb, bw["f2w"], dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=a["hpre"])
+            call("dig_colsum", dh, 0, 4 * d, grads[nm + "mlp.fc1.bias"], None, M, 4 * d)
+            ops.gemm(dh, a["ln2"], grads[nm + "mlp.fc1.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(4 * d, d, M))
+            ops.gemm(dh, bw["f1w"], dln, b_mn_major=True)
+            call("dig_layernorm_bwd", dln, a["xm"], a["mean2"], a["rstd2"], bw["n2w"], None, g, g, gb,
+                 grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], M, d, 0)
+            # ---- attention (F:87-125) ----
+            call("dig_colsum", gb, 0, d, grads[nm + "attn.proj.bias"], None, M, d)
+            ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(d, d, M))
+            ops.gemm(gb, bw["pw"], dat, b_mn_major=True)
+            ops.attention_bwd(a["qkv"], a["att"], dat, a["lse"], dqkv, h, self.scale)
+            dqkvb.zero_()
+            call("dig_colsum", dqkv, 0, 3 * d, dqkvb, None, M, 3 * d)
+            grads[nm + "attn.q_bias"].copy_(dqkvb[:d])
+            grads[nm + "attn.v_bias"].copy_(dqkvb[2 * d:])
+            ops.gemm(dqkv, a["ln1"], grads[nm + "attn.qkv.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(3 * d, d, M))
+            ops.gemm(dqkv, bw["qkvw"], dln, b_mn_major=True)
+            call("dig_layernorm_bwd", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], None, g, g, gb,
+                 grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], M, d, 0)
+        # ---- patch embed + mask token (F:190-196, V:95-99); pos_embed carries no gradient (V:99 detach) ----
+        pre = W["pre"]
+        gz = B.get("bw.gz", (M, d), BF16)
+        call("dig_zero_masked_rows", g, sv["mask"], gz, M, d)
+        call("dig_colsum", gz, 0, d, grads[pre + "patch_embed.proj.bias"], None, M, d)
+        tot = B.get("bw.tot", (d,), F32)
+        tot.zero_()
+        call("dig_colsum", g, 1, d, tot, None, M, d)
+        torch.sub(tot, grads[pre + "patch_embed.proj.bias"], out=grads[pre + "mask_token"].view(-1))
+        ops.gemm(gz, sv["a0"], grads[pre + "patch_embed.proj.weight"].view(d, 48), a_mn_major=True, b_mn_major=True,
+                 split_k=_split_k(d, 48, M, 64))
+
+    # ------------------------------------------------------------------ BatchNorm MLP heads (M:463-482)
+    def _mlp_layers(self, prefix, num_layers, seq):
+        return [(self.shadow["%s%d.weight" % (prefix, 3 * i)], seq[3 * i + 1], "%s%d.weight" % (prefix, 3 * i),
+                 "%s%d." % (prefix, 3 * i + 1)) for i in range(num_layers)]
+
+    def _mlp_fwd(self, x_bf16, layers, tag, want_bf16_out=False):
+        B = self.bufs
+        rows = x_bf16.shape[0]
+        world, _ = _world()
+        saved, a = [], x_bf16
+        out_f32 = None
+        for li, (w, bn, _, _) in enumerate(layers):
+            last = li == len(layers) - 1
+            C = w.shape[0]
+            z = B.get("%s.z%d" % (tag, li), (rows, C), F32)
+            ops.gemm(a, w, z)
+            stats = B.get("%s.st%d" % (tag, li), (2 * C,), F32)
+            stats.zero_()
+            call("dig_colsum", z, 1, C, stats, stats[C:], rows, C)
+            count = float(rows)
+            if self._bn_sync(bn):
+                dist.all_reduce(stats)
+                count = float(rows * world)
+            a_out = B.get("%s.a%d" % (tag, li), (rows, C), BF16) if (not last or want_bf16_out) else None
+            out_f32 = B.get("%s.out" % tag, (rows, C), F32) if last else None
+            gamma, beta = (bn.weight, bn.bias) if bn.affine else (None, None)
+            call("dig_bn_apply", z, stats, count, gamma, beta, 0 if last else 1, bn.eps, a_out, out_f32, rows, C)
+            if bn.track_running_stats and bn.running_mean is not None:
+                mom = 0.1 if bn.momentum is None else bn.momentum
+                call("dig_bn_running", stats, count, mom, bn.running_mean, bn.running_var, bn.num_batches_tracked, C)
+            saved.append(dict(a_in=a, z=z, stats=stats, count=count, a_out=a_out))
+            a = a_out
+        return out_f32, a, saved
+
+    def _mlp_bwd(self, dy, layers, saved, tag, grads, dx_out):
+        """dy fp32 [rows, C_last] w.r.t. the last BatchNorm output.  Writes d input (fp32) into dx_out when given."""
+        B = self.bufs
+        rows = dy.shape[0]
+        for li in reversed(range(len(layers))):
+            w, bn, wname, bnname = layers[li]
+            sv = saved[li]
+            C = w.shape[0]
+            bst = B.get("%s.bst%d" % (tag, li), (2 * C,), F32)
+            bst.zero_()
+            call("dig_bn_bwd_stats", dy, sv["z"], sv["stats"], sv["count"], bn.eps, bst, rows, C)
+            if bn.affine:
+                grads[bnname + "bias"].copy_(bst[:C])
+                grads[bnname + "weight"].copy_(bst[C:])
+            if self._bn_sync(bn):
+                dist.all_reduce(bst)
+            dz = B.get("%s.dz%d" % (tag, li), (rows, C), BF16)
+            call("dig_bn_bwd_apply", dy, sv["z"], sv["stats"], bst, sv["count"], bn.weight if bn.affine else None, bn.eps, dz, None, rows, C)
+            a_in = sv["a_in"]
+            Cin = a_in.shape[1]
+            ops.gemm(dz, a_in, grads[wname], a_mn_major=True, b_mn_major=True, split_k=_split_k(C, Cin, rows))
+            if li > 0:
+                dy = B.get("%s.dy%d" % (tag, li), (rows, Cin), F32)
+                ops.gemm(dz, w, dy, b_mn_major=True, epilogue=ops.EPI_RELU_MASK, aux=a_in)
+            elif dx_out is not None:
+                ops.gemm(dz, w, dx_out, b_mn_major=True)
+
+    # ------------------------------------------------------------------ forward (M:488-577)
+    def forward(self, image, aug_image, vis_mask_pos, m, only_mim_on_ori_img, need_grad=True):
+        model, Bf = self.model, self.bufs
+        dev, d = self.device, self.d
+        Bsz = image.shape[0]
+        S, M, half = 2 * Bsz, 2 * Bsz * TOK, Bsz * TOK
+        world, rank = _world()
+        if vis_mask_pos.dim() != 3 or vis_mask_pos.shape[0] != Bsz or vis_mask_pos.shape[-1] != TOK:
+            raise ops.DigError("vis_mask_pos must be [B, num_view, 256], got %s" % (tuple(vis_mask_pos.shape),))
+        if not only_mim_on_ori_img:
+            raise ops.DigError("only_mim_on_ori_img=False is not built (README.md:75 runs with --only_mim_on_ori_img 1)")
+        if vis_mask_pos.shape[1] != 2:
+            raise ops.DigError("num_view must be 2 (README.md:66), got %d" % vis_mask_pos.shape[1])
+        images = Bf.get("images", (S, 3, 32, 128), F32)
+        images[:Bsz].copy_(image)
+        images[Bsz:].copy_(aug_image)
+        mask_u8 = Bf.get("mask", (M,), torch.uint8)
+        mask_u8.view(2, Bsz, TOK).copy_(vis_mask_pos.permute(1, 0, 2))      # M:496-497 view-major
+
+        # bf16 shadows of the online weights + fused qkv bias
+        self._mt("dig_mt_cast_bf16", self.tab_cast_online)
+        if not self.momentum_warm:
+            self._mt("dig_mt_cast_bf16", self.tab_cast_momentum)
+            self.momentum_warm = True
+        # ---- momentum branch first in stream order is fine: it only depends on the pre-step online weights ----
+        self._mt("dig_mt_ema", self.tab_ema, float(m))                       # M:526 (before the momentum forward)
+        self._mt("dig_mt_copy_f32", self.tab_qkv_bias)
+
+        Wm = self._enc_weights("momentum_encoder.")
+        enc_m, _ = self._encoder_fwd(Wm, images, mask_u8, "m.", save=False)
+        a0 = Bf.get("m.pp.in", (half, d), BF16)
+        call("dig_cast_f32_bf16", enc_m, a0, half * d)
+        ppm_layers = self._mlp_layers("pix_projector_m.", 3, model.pix_projector_m)
+        ppm_out, _, _ = self._mlp_fwd(a0, ppm_layers, "m.pp")
+        pooled_m = Bf.get("m.pooled", (S * self.num_windows, d), BF16)
+        call("dig_pool_fwd", ppm_out, enc_m[half:], Bsz, pooled_m, S, d, self.num_windows)
+        k, _, _ = self._mlp_fwd(pooled_m, self._mlp_layers("momentum_projection_layer.", 3, model.momentum_projection_layer), "m.proj")
+        R = k.shape[0]            # 2 * B * num_windows rows: [k1 ; k2]
+        Q, C = R // 2, k.shape[1]
+        kn = Bf.get("kn", (R, C), F32)
+        call("dig_l2norm_fwd", k, kn, None, R, C)
+        if world > 1:                                                        # concat_all_gather, M:580-591
+            kall = Bf.get("kall", (world, R, C), F32)
+            dist.all_gather_into_tensor(kall, kn)
+            k1_all = Bf.get("k1all", (world * Q, C), F32)
+            k2_all = Bf.get("k2all", (world * Q, C), F32)
+            k1_all.view(world, Q, C).copy_(kall[:, :Q])
+            k2_all.view(world, Q, C).copy_(kall[:, Q:])
+        else:
+            k1_all, k2_all = kn[:Q], kn[Q:]
+
+        # ---- online branch ----
+        W = self._enc_weights("encoder.")
+        enc, sv_enc = self._encoder_fwd(W, images, mask_u8, "o.", save=True)
+        pp_in = Bf.get("o.pp.in", (half, d), BF16)
+        call("dig_cast_f32_bf16", enc, pp_in, half * d)
+        pp_layers = self._mlp_layers("pix_projector.", 3, model.pix_projector)
+        pp_out, _, sv_pp = self._mlp_fwd(pp_in, pp_layers, "o.pp")
+        pooled = Bf.get("o.pooled", (S * self.num_windows, d), BF16)
+        call("dig_pool_fwd", pp_out, enc[half:], Bsz, pooled, S, d, self.num_windows)
+        proj_layers = self._mlp_layers("encoder_projection_layer.", 3, model.encoder_projection_layer)
+        _, proj_bf16, sv_proj = self._mlp_fwd(pooled, proj_layers, "o.proj", want_bf16_out=True)
+        pred_layers = self._mlp_layers("predictor.", 2, model.predictor)
+        q, _, sv_pred = self._mlp_fwd(proj_bf16, pred_layers, "o.pred")
+        qn = Bf.get("qn", (R, C), F32)
+        qinv = Bf.get("qinv", (R,), F32)
+        call("dig_l2norm_fwd", q, qn, qinv, R, C)
+
+        # ---- contrastive loss (M:444-461): q1.k2 + q2.k1 ----
+        Nk = world * Q
+        res = Bf.get("nce.res", (2, 4), F32)
+        res.zero_()
+        lg1 = Bf.get("nce.lg1", (Q, Nk), F32)
+        lg2 = Bf.get("nce.lg2", (Q, Nk), F32)
+        call("dig_sgemm_f32", qn[:Q], k2_all, lg1, Q, Nk, C, 1, 1.0 / self.T)
+        call("dig_sgemm_f32", qn[Q:], k1_all, lg2, Q, Nk, C, 1, 1.0 / self.T)
+        call("dig_infonce_rows", lg1, Q, Nk, Q * rank, self.T, res[0])
+        call("dig_infonce_rows", lg2, Q, Nk, Q * rank, self.T, res[1])
+
+        # ---- masked-pixel decoder on the masked rows of view 0 (M:561-570; row-wise, so gather first) ----
+        n_per = self._masked_per_sample(vis_mask_pos)
+        n_m = Bsz * n_per
+        idx = Bf.get("dec.idx", (max(n_m, 1),), torch.int32)
+        err = Bf.get("dec.err", (1,), torch.int32)
+        err.zero_()
+        call("dig_mask_to_index", mask_u8, idx, err, Bsz, n_per)
+        g0 = Bf.get("dec.g0", (n_m, d), BF16)
+        call("dig_gather_rows", enc, idx, g0, n_m, d)
+        S_ = self.shadow
+        t1 = Bf.get("dec.t1", (n_m, 192), BF16)
+        ops.gemm(g0, S_["pix_decoder.0.weight"], t1)
+        t2 = Bf.get("dec.t2", (n_m, 192), F32)
+        ops.gemm(t1, S_["pix_decoder.1.weight"], t2)
+        t3 = Bf.get("dec.t3", (n_m, 192), BF16)
+        dmean, drstd = Bf.get("dec.mean", (n_m,), F32), Bf.get("dec.rstd", (n_m,), F32)
+        ln = model.pix_decoder[2]
+        self._ln(t2, ln.weight, ln.bias, t3, dmean, drstd, gelu=1, eps=ln.eps)
+        vis = torch.empty(n_m, 48, dtype=F32, device=dev)
+        ops.gemm(t3, S_["pix_decoder.4.weight"], vis, bias=self._named["pix_decoder.4.bias"])
+
+        self.saved = dict(enc=sv_enc, W=W, pp=(pp_layers, sv_pp), proj=(proj_layers, sv_proj), pred=(pred_layers, sv_pred),
+                          qn=qn, qinv=qinv, k1_all=k1_all, k2_all=k2_all, lg1=lg1, lg2=lg2, Q=Q, Nk=Nk, C=C, Bsz=Bsz,
+                          idx=idx, n_m=n_m, g0=g0, t1=t1, t2=t2, t3=t3, dmean=dmean, drstd=drstd, pooled=pooled)
+        contra = res[:, 0].sum()
+        accs = res[:, 1:3].clone()      # [[q1_acc1, q1_acc5], [q2_acc1, q2_acc5]]
+        return contra, vis.view(Bsz, n_per, 48), accs
+
+    def _masked_per_sample(self, vis_mask_pos):
+        key = (tuple(vis_mask_pos.shape), vis_mask_pos.data_ptr() if False else 0)
+        if key not in self._n_masked:
+            cnt = vis_mask_pos[:, 0].sum(dim=1)
+            n = int(cnt[0].item())
+            if not bool((cnt == n).all().item()):
+                raise ops.DigError("every sample must mask the same number of patches (masking_generator.py:20)")
+            self._n_masked[key] = n
+        return self._n_masked[key]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, d_contra, d_vis):
+        """d_contra: 0-d fp32 tensor or None; d_vis: fp32 [B, n, 48] or None.  Returns gradients in trainable_params() order."""
+        sv, Bf, model = self.saved, self.bufs, self.model
+        if sv is None:
+            raise ops.DigError("backward called without a saved forward")
+        d, Bsz = self.d, sv["Bsz"]
+        S, M, half = 2 * Bsz, 2 * Bsz * TOK, Bsz * TOK
+        flat = torch.zeros(self.grad_total, dtype=F32, device=self.device)
+        grads = self._grad_views(flat)
+        g = Bf.get("bw.g", (M, d), F32)
+        S_ = self.shadow
+
+        # ---- contrastive head ----
+        if d_contra is not None:
+            Q, Nk, C = sv["Q"], sv["Nk"], sv["C"]
+            R = 2 * Q
+            dqn = Bf.get("bw.dqn", (R, C), F32)
+            call("dig_sgemm_f32", sv["lg1"], sv["k2_all"], dqn[:Q], Q, C, Nk, 0, 1.0)
+            call("dig_sgemm_f32", sv["lg2"], sv["k1_all"], dqn[Q:], Q, C, Nk, 0, 1.0)
+            dq = Bf.get("bw.dq", (R, C), F32)
+            gs = d_contra.reshape(1).to(F32).contiguous()
+            call("dig_l2norm_bwd", dqn, sv["qn"], sv["qinv"], gs, dq, R, C)
+            dproj = Bf.get("bw.dproj", (R, C), F32)
+            self._mlp_bwd(dq, sv["pred"][0], sv["pred"][1], "bw.pred", grads, dproj)
+            dpooled = Bf.get("bw.dpooled", (R, d), F32)
+            self._mlp_bwd(dproj, sv["proj"][0], sv["proj"][1], "bw.proj", grads, dpooled)
+            dpp = Bf.get("bw.dpp", (half, d), F32)
+            call("dig_pool_bwd", dpooled, Bsz, dpp, g[half:], S, d, self.num_windows)
+            self._mlp_bwd(dpp, sv["pp"][0], sv["pp"][1], "bw.pp", grads, g[:half])
+        else:
+            g.zero_()
+
+        # ---- masked-pixel decoder ----
+        if d_vis is not None:
+            n_m = sv["n_m"]
+            dv = Bf.get("bw.dvis", (n_m, 48), BF16)
+            dvf = d_vis.reshape(n_m, 48).to(F32).contiguous()
+            call("dig_cast_f32_bf16", dvf, dv, n_m * 48)
+            call("dig_colsum", dv, 0, 48, grads["pix_decoder.4.bias"], None, n_m, 48)
+            ops.gemm(dv, sv["t3"], grads["pix_decoder.4.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(48, 192, n_m, 64))
+            dt3 = Bf.get("bw.dt3", (n_m, 192), BF16)
+            ops.gemm(dv, S_["pix_decoder.4.weight"], dt3, b_mn_major=True)
+            dt2 = Bf.get("bw.dt2", (n_m, 192), BF16)
+            ln = model.pix_decoder[2]
+            call("dig_layernorm_bwd", dt3, sv["t2"], sv["dmean"], sv["drstd"], ln.weight, ln.bias, None, None, dt2,
+                 grads["pix_decoder.2.weight"], grads["pix_decoder.2.bias"], n_m, 192, 1)
+            ops.gemm(dt2, sv["t1"], grads["pix_decoder.1.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(192, 192, n_m, 64))
+            dt1 = Bf.get("bw.dt1", (n_m, 192), BF16)
+            ops.gemm(dt2, S_["pix_decoder.1.weight"], dt1, b_mn_major=True)
+            ops.gemm(dt1, sv["g0"], grads["pix_decoder.0.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(192, d, n_m, 64))
+            dg0 = Bf.get("bw.dg0", (n_m, d), F32)
+            ops.gemm(dt1, S_["pix_decoder.0.weight"], dg0, b_mn_major=True)
+            call("dig_scatter_add_rows", dg0, sv["idx"], g, n_m, d)
+
+        # ---- encoder ----
+        gb = Bf.get("bw.gb", (M, d), BF16)
+        call("dig_cast_f32_bf16", g, gb, M * d)
+        self._encoder_bwd(sv["W"], sv["enc"], g, gb, grads)
+        self.saved = None
+        return [grads[n] for n in self.train_names]
+
+
+class _PretrainFn(torch.autograd.Function):
+    """One autograd node for the whole model: gradients reach ordinary leaf nn.Parameters (DDP-compatible)."""
+
+    @staticmethod
+    def forward(ctx, step, image, aug_image, vis_mask_pos, m, only_mim, *params):
+        contra, vis, accs = step.forward(image, aug_image, vis_mask_pos, m, only_mim)
+        ctx.step = step
+        ctx.mark_non_differentiable(accs)
+        return contra, vis, accs
+
+    @staticmethod
+    def backward(ctx, d_contra, d_vis, _d_accs):
+        grads = ctx.step.backward(d_contra, d_vis)
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
+def run_model(step, image, aug_image, vis_mask_pos, m, only_mim_on_ori_img):
+    params = step.trainable_params()
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        contra, vis, accs = _PretrainFn.apply(step, image, aug_image, vis_mask_pos, m, only_mim_on_ori_img, *params)
+    else:
+        contra, vis, accs = step.forward(image, aug_image, vis_mask_pos, m, only_mim_on_ori_img)
+    return {"contra_loss": contra, "q1_acc1": accs[0, 0:1], "q1_acc5": accs[0, 1:2], "q2_acc1": accs[1, 0:1],
+            "q2_acc5": accs[1, 1:2], "vis_out": [vis]}

@@ -65,6 +65,88 @@ int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t num_seqs, 
 int dig_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                       int64_t num_seqs, int32_t heads, float scale, void* stream);
 
+/* ---- HBM-bound row / column kernels ---------------------------------------------------------------- */
+/* 4x4/stride-4 patch extraction for the patch-embed GEMM (F:188-195): images fp32 [n,3,32,128] ->
+ * bf16 [n*256, 48], column k = c*16 + kh*4 + kw (the conv-weight order).                           */
+int dig_im2col_patch4(const float* images, void* out, int64_t num_images, void* stream);
+/* nn.LayerNorm(eps) forward (F:134,140; M:424): x fp32 [rows,d] -> y bf16; optional gelu(y) (M:424-425);
+ * mean/rstd fp32 [rows] are saved for the backward (may be NULL).  d % 64 == 0, d <= 512.            */
+int dig_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                      int64_t rows, int32_t d, float eps, int32_t gelu, void* stream);
+/* LayerNorm backward: dx = dres + dLN(dy) written as fp32 and/or bf16 (either may be NULL), dgamma/dbeta
+ * accumulated (+=).  dy is bf16, w.r.t. the LN output (or the GELU(LN) output when gelu != 0).       */
+int dig_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                      int64_t rows, int32_t d, int32_t gelu, void* stream);
+/* PatchNet pooling without patch transformer (M:189-193): [S,8,32,d] fp32 -> mean over 8 x (32/num_windows)
+ * token windows -> bf16 [S*num_windows, d].  Sequences < split come from x0, the others from x1.     */
+int dig_pool_fwd(const float* x0, const float* x1, int64_t split, void* out, int64_t num_seqs, int32_t d,
+                 int32_t num_windows, void* stream);
+int dig_pool_bwd(const float* dpool, int64_t split, float* dx0, float* dx1, int64_t num_seqs, int32_t d,
+                 int32_t num_windows, void* stream);
+/* boolean-mask row selection of M:569 as an index gather (fp32 -> bf16) and its backward (+=).       */
+int dig_gather_rows(const float* x, const int32_t* idx, void* out, int64_t n, int32_t d, void* stream);
+int dig_scatter_add_rows(const float* src, const int32_t* idx, float* dst, int64_t n, int32_t d, void* stream);
+/* out[c] += sum_r x[r,c] (bias gradients); with out_sq also out_sq[c] += sum_r x[r,c]^2 (BatchNorm statistics). */
+int dig_colsum(const void* x, int32_t x_is_fp32, int64_t ld, float* out, float* out_sq, int64_t rows, int32_t cols,
+               void* stream);
+/* nn.BatchNorm1d in training mode (M:463-482; SyncBatchNorm under DDP, R:390).  stats = [sum | sumsq] fp32 [2C]
+ * over `count` rows -- the caller all-reduces stats across ranks between dig_colsum and dig_bn_apply.       */
+int dig_bn_apply(const float* x, const float* stats, float count, const float* gamma, const float* beta, int32_t relu,
+                 float eps, void* y_bf16, float* y_f32, int64_t rows, int32_t C, void* stream);
+int dig_bn_running(const float* stats, float count, float momentum, float* running_mean, float* running_var,
+                   int64_t* num_batches_tracked, int32_t C, void* stream);
+/* bstats = [sum dy | sum dy*xhat] (+=), then dx = gamma*rstd*(dy - bstats0/count - xhat*bstats1/count).       */
+int dig_bn_bwd_stats(const float* dy, const float* x, const float* stats, float count, float eps, float* bstats,
+                     int64_t rows, int32_t C, void* stream);
+int dig_bn_bwd_apply(const float* dy, const float* x, const float* stats, const float* bstats, float count,
+                     const float* gamma, float eps, void* dx_bf16, float* dx_f32, int64_t rows, int32_t C, void* stream);
+
+/* elementwise fp32 -> bf16 (n % 4 == 0). */
+int dig_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+/* y (bf16 [rows,d]) = row_mask[r] ? 0 : x[r,:]  -- gradient that reaches the patch-embed GEMM past the mask-token mix (V:95-97). */
+int dig_zero_masked_rows(const float* x, const uint8_t* row_mask, void* y, int64_t rows, int32_t d, void* stream);
+/* Boolean mask [B,256] -> row indices in boolean-mask order (M:569): idx[b*n_per+j] = b*256 + j-th set position;
+ * err[0] = 1 if some sample does not have exactly n_per set bits.                                       */
+int dig_mask_to_index(const uint8_t* mask, int32_t* idx, int32_t* err, int32_t B, int32_t n_per, void* stream);
+
+/* ---- losses (fp32) --------------------------------------------------------------------------------- */
+/* F.normalize(x, dim=1) (M:446-447) and its backward, dx = (dy - y<y,dy>) * inv_norm * gscale[0] (gscale may be NULL). */
+int dig_l2norm_fwd(const float* x, float* y, float* inv_norm, int64_t rows, int32_t C, void* stream);
+int dig_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, const float* gscale, float* dx, int64_t rows,
+                   int32_t C, void* stream);
+/* fp32 GEMM for the InfoNCE logits einsum('nc,mc->nm') (M:451) and its gradient: C = alpha * A[M,K] . B, with B given
+ * as [N,K] (b_is_nk) or [K,N].                                                                        */
+int dig_sgemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t b_is_nk, float alpha,
+                  void* stream);
+/* Row pass of contrastive_loss (M:453-461, M:593-625) on logits[Q,Nk] = q.k^T/T: result[0] += CE*2T (mean over Q),
+ * result[1]/[2] += top-1/top-5 accuracy in percent; logits are overwritten with d loss / d (q.k^T).    */
+int dig_infonce_rows(float* logits, int32_t Q, int32_t Nk, int64_t label_offset, float T, float* result, void* stream);
+/* Masked-pixel MSE (E:85-111 target build + E:141 F.mse_loss): pred fp32 [n_rows,48]; idx[r] = b*256 + token of view 0;
+ * images fp32 [B,3,32,128] normalised with mean=std=0.5; loss[0] += mse; dpred (may be NULL) = d mse / d pred. */
+int dig_masked_mse(const float* pred, const float* images, const int32_t* idx, float* loss, float* dpred, int64_t n_rows,
+                   void* stream);
+int dig_scale_by_device_scalar(const float* x, const float* s, float* y, int64_t n, void* stream);
+
+/* ---- multi-tensor parameter kernels (pointer tables on the device, see dig_b200/csrc/optim.cu) ------ */
+int dig_mt_chunk(void); /* elements per thread block in the blk_* tables */
+int dig_mt_cast_bf16(const int64_t* src, const int64_t* dst, const int64_t* numel, const int32_t* blk_tensor,
+                     const int32_t* blk_chunk, int32_t num_blocks, void* stream);
+int dig_mt_copy_f32(const int64_t* src, const int64_t* dst, const int64_t* numel, const int32_t* blk_tensor,
+                    const int32_t* blk_chunk, int32_t num_blocks, void* stream);
+/* _update_momentum_encoder (M:428-442): target = m*target + (1-m)*online; shadow (bf16, may be NULL) = target. */
+int dig_mt_ema(const int64_t* online, const int64_t* target, const int64_t* shadow, const int64_t* numel,
+               const int32_t* blk_tensor, const int32_t* blk_chunk, int32_t num_blocks, float m, void* stream);
+/* out[0] += sum of squares over all tensors (get_grad_norm_, U:507-519). */
+int dig_mt_sumsq(const int64_t* src, const int64_t* numel, const int32_t* blk_tensor, const int32_t* blk_chunk,
+                 int32_t num_blocks, float* out, void* stream);
+/* AdamW (custom_optim/_functional.py:115-140) with per-tensor lr / weight_decay, gradient unscale (grad_scale) and
+ * optional clip_grad_norm_ (max_norm > 0, sumsq[0] = squared norm of the scaled grads); refreshes the bf16 shadow. */
+int dig_mt_adamw(const int64_t* params, const int64_t* grads, const int64_t* exp_avg, const int64_t* exp_avg_sq,
+                 const int64_t* shadow, const int64_t* numel, const float* lr, const float* weight_decay,
+                 const int32_t* blk_tensor, const int32_t* blk_chunk, int32_t num_blocks, float beta1, float beta2,
+                 float eps, int64_t step, float grad_scale, const float* sumsq, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
