@@ -1,0 +1,142 @@
+"""Drop-in boundary B2: `train_one_epoch` with the reference's signature and return value
+(engine_for_pretraining_moco.py:26-204, tag E), re-sequenced for the B200 path:
+
+  * target build + masked gather + MSE (E:83-111, E:141) is ONE kernel (dig_masked_mse) that patchifies
+    the un-normalised view-0 pixels on the fly;
+  * the model call is one autograd node running the sm_100a kernels (no autocast: operands are bf16 by
+    construction, statistics / losses fp32);
+  * the ~10 blocking `.item()` reads per step (E:123-176) are replaced by ONE packed device->host copy.
+"""
+import math
+import sys
+
+import numpy as np
+import torch
+
+from . import ops, utils
+from .ops import call
+
+
+class _MaskedPixelMSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, images, idx):
+        n_rows = idx.numel()
+        p = pred.reshape(n_rows, 48).contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        dpred = torch.empty_like(p)
+        call("dig_masked_mse", p, images, idx, loss, dpred, n_rows)
+        ctx.save_for_backward(dpred)
+        ctx.shape = pred.shape
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        out = torch.empty_like(dpred)
+        call("dig_scale_by_device_scalar", dpred, g.reshape(1).to(torch.float32).contiguous(), out, dpred.numel())
+        return out.view(ctx.shape), None, None
+
+
+def masked_pixel_mse(pred, images, mask_view0):
+    """F.mse_loss(pred, patchify(unnormalise(images))[mask]) (E:85-111,141).  pred fp32 [B,n,48]; images fp32 [B,3,32,128]
+    normalised with mean=std=0.5; mask_view0 bool/uint8 [B,256] with exactly n set positions per sample."""
+    B, n = pred.shape[0], pred.shape[1]
+    if not pred.is_cuda:
+        raise ops.DigError("masked_pixel_mse runs on CUDA tensors only")
+    idx = torch.empty(B * n, dtype=torch.int32, device=pred.device)
+    err = torch.zeros(1, dtype=torch.int32, device=pred.device)
+    call("dig_mask_to_index", mask_view0.to(torch.uint8).contiguous(), idx, err, B, n)
+    return _MaskedPixelMSE.apply(pred, images.contiguous(), idx)
+
+
+def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader, word_data_loader, optimizer, device, epoch,
+                    loss_scaler, max_norm=0, patch_size=16, normlize_target=True, log_writer=None, lr_scheduler=None,
+                    start_steps=None, lr_schedule_values=None, wd_schedule_values=None, momentum_schedule=None, args=None):
+    """Same contract as E:26-204.  `teacher_model`, `teacher_model_without_ddp`, `word_data_loader` and
+    `momentum_schedule` are accepted and unused, exactly as in the reference."""
+    if normlize_target:
+        raise NotImplementedError("normlize_target=True (per-patch normalised targets, E:89-94) is not built; the README "
+                                  "configuration runs with the raw-pixel target (run_mae_pretraining_moco.py:90 default False)")
+    if patch_size != 4:
+        raise ops.DigError("patch_size must be 4 (pretrain_*_patch4_32x128), got %r" % (patch_size,))
+    model.train()
+    metric_logger = utils.MetricLogger(delimiter="  ")
+    metric_logger.add_meter("lr", utils.SmoothedValue(window_size=1, fmt="{value:.6f}"))
+    metric_logger.add_meter("min_lr", utils.SmoothedValue(window_size=1, fmt="{value:.6f}"))
+    header = "Epoch: [{}]".format(epoch)
+    print_freq = 100
+    if args.num_view != 2:
+        raise ops.DigError("num_view must be 2 (README.md:66)")
+    n_it = len(data_loader)
+    start_steps = 0 if start_steps is None else start_steps
+
+    # contrast loss weight warm-up table, E:47-56
+    if epoch == args.contrast_start_epoch:
+        k = min(args.contrast_warmup_steps, n_it)
+        w = np.linspace(0.0, args.loss_weight_contrast, k)
+        if k < n_it:
+            w = np.hstack([w, np.ones(n_it - k) * args.loss_weight_contrast])
+    elif epoch > args.contrast_start_epoch:
+        w = np.ones(n_it) * args.loss_weight_contrast
+    else:
+        w = np.zeros(n_it)
+
+    for step, (batch, text, text_lens) in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
+        it = start_steps + step
+        if lr_schedule_values is not None or wd_schedule_values is not None:                      # E:60-66
+            for group in optimizer.param_groups:
+                if lr_schedule_values is not None:
+                    group["lr"] = lr_schedule_values[it] * group["lr_scale"]
+                if wd_schedule_values is not None and group["weight_decay"] > 0:
+                    group["weight_decay"] = wd_schedule_values[it]
+        moco_m = utils.adjust_moco_momentum(epoch + 1.0 * step / n_it, args) if args.use_moco_m_cos else args.moco_m
+        metric_logger.update(moco_m=moco_m)
+
+        images, aug_images, mask = batch
+        images = images.to(device, non_blocking=True)
+        aug_images = aug_images.to(device, non_blocking=True)
+        mask = mask.to(device, non_blocking=True).flatten(1).to(torch.bool).view(images.shape[0], args.num_view, -1)
+        if args.only_mim_on_ori_img:
+            mask[:, 1, :].fill_(0)                                                                    # E:103-104
+
+        out = model(images, aug_images, mask, moco_m, args.only_mim_on_ori_img)
+        contra = out["contra_loss"]
+        loss_pixel = masked_pixel_mse(out["vis_out"][0], images, mask[:, 0])
+        loss = contra * float(w[step]) + loss_pixel * float(args.loss_weight_pixel)
+
+        optimizer.zero_grad()
+        grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=model.parameters(), create_graph=False)
+        loss_scale_value = loss_scaler.state_dict()["scale"]
+
+        # one packed device->host read per step (the reference blocks ~10 times, E:123-176)
+        packed = torch.stack([loss.detach().float().reshape(()), contra.detach().float().reshape(()), loss_pixel.detach().reshape(()),
+                              out["q1_acc1"].reshape(()), out["q1_acc5"].reshape(()), out["q2_acc1"].reshape(()),
+                              out["q2_acc5"].reshape(()), grad_norm.to(loss.device).float().reshape(())]).tolist()
+        loss_value = packed[0]
+        if not math.isfinite(loss_value):                                                             # E:148-150
+            print("Loss is {}, stopping training".format(loss_value))
+            sys.exit(1)
+        metric_logger.update(loss_contrast=packed[1], q1_acc1=packed[3], q1_acc5=packed[4], q2_acc1=packed[5], q2_acc5=packed[6],
+                             loss_pixel=packed[2], loss=loss_value, loss_scale=loss_scale_value)
+        lrs = [g["lr"] for g in optimizer.param_groups]
+        wds = [g["weight_decay"] for g in optimizer.param_groups if g["weight_decay"] > 0]
+        metric_logger.update(lr=max(lrs), min_lr=min(lrs), weight_decay=wds[-1] if wds else None, grad_norm=packed[7])
+        if log_writer is not None:
+            log_writer.update(loss=loss_value, head="loss")
+            log_writer.update(loss_scale=loss_scale_value, head="opt")
+            log_writer.update(lr=max(lrs), head="opt")
+            log_writer.update(min_lr=min(lrs), head="opt")
+            log_writer.update(weight_decay=wds[-1] if wds else None, head="opt")
+            log_writer.update(grad_norm=packed[7], head="opt")
+            log_writer.set_step()
+        if lr_scheduler is not None:
+            lr_scheduler.step_update(start_steps + step)
+        if step >= 1 and step % (args.eval_freq * 10) == 0 and getattr(args, "output_dir", None):
+            from .checkpoint import save_model
+            save_model(args=args, model=model, model_without_ddp=getattr(model, "module", model), optimizer=optimizer,
+                       loss_scaler=loss_scaler, epoch="{0}_{1}".format(epoch, step))
+        sys.stdout.flush()
+
+    metric_logger.synchronize_between_processes()
+    print("Averaged stats:", metric_logger)
+    return {k: meter.global_avg for k, meter in metric_logger.meters.items()}

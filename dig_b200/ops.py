@@ -86,11 +86,37 @@ def load():
     return lib
 
 
+_launches = 0
+_gemm_prof = None   # None, or a list of (event0, event1, flops) while profiling
+
+
+def launch_count():
+    """Number of dig_b200 kernels launched through this binding so far (one per C-ABI compute call)."""
+    return _launches
+
+
+def count_launch(n=1):
+    global _launches
+    _launches += n
+
+
+def profile_gemm(enable):
+    """Per-launch CUDA-event timing of dig_gemm.  profile_gemm(True) starts; profile_gemm(False) -> (flops, ms, launches)."""
+    global _gemm_prof
+    if enable:
+        _gemm_prof = []
+        return None
+    torch.cuda.synchronize()
+    rec, _gemm_prof = _gemm_prof or [], None
+    return (sum(f for _, _, f in rec), sum(a.elapsed_time(b) for a, b, _ in rec), len(rec))
+
+
 def call(name, *args):
     """Generic C-ABI call: torch tensors are passed by data_ptr(), None as NULL; the current stream is appended."""
     lib = load()
     conv = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
     rc = getattr(lib, name)(*conv, torch.cuda.current_stream().cuda_stream)
+    count_launch()
     if rc != 0:
         raise DigError("%s failed (%d): %s" % (name, rc, lib.dig_last_error().decode()))
 
@@ -158,7 +184,15 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
         g.aux, g.ldaux = aux.data_ptr(), aux.stride(0)
     g.alpha = alpha
     g.split_k = split_k
-    _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")
+    if _gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")
+        e1.record()
+        _gemm_prof.append((e0, e1, 2.0 * M * N * K))
+    else:
+        _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")
+    count_launch()
     return out
 
 
@@ -175,6 +209,7 @@ def attention_fwd(qkv, out, lse, heads, scale, p_in_smem=False):
             raise DigError("attention_fwd: lse must hold [S, heads, 256]")
     _check(load().dig_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), rows // 256, heads, scale, int(p_in_smem), _stream()),
            "dig_attention_fwd")
+    count_launch()
     return out
 
 
@@ -191,4 +226,5 @@ def attention_bwd(qkv, out, dout, lse, dqkv, heads, scale):
         raise DigError("attention_bwd: bad shapes")
     _check(load().dig_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), rows // 256, heads, scale, _stream()),
            "dig_attention_bwd")
+    count_launch()
     return dqkv

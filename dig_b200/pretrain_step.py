@@ -179,6 +179,7 @@ class PretrainStep:
         lib = ops.load()
         rc = getattr(lib, fn)(*[t.data_ptr() for t in tab.ptrs], tab.numel.data_ptr(), tab.blk_tensor.data_ptr(),
                               tab.blk_chunk.data_ptr(), tab.num_blocks, *extra, torch.cuda.current_stream().cuda_stream)
+        ops.count_launch()
         if rc != 0:
             raise ops.DigError("%s failed: %s" % (fn, lib.dig_last_error().decode()))
 
