@@ -59,12 +59,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// exact (erf) GELU and its derivative, fp32
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf(x) ~= x P(x^2) / Q(x^2) on |x| <= 3.925 (clamped beyond), max abs error 3.9e-7 in fp32: one MUFU (rcp) + 12 FMA.
+// Coefficients fitted against scipy.special.erf (all positive, Q >= 1, so no cancellation or poles).
+__device__ __forceinline__ float erf_fast(float x) {
+  x = fminf(fmaxf(x, -3.925f), 3.925f);
+  const float t = x * x;
+  float p = 2.057485900e-06f;
+  p = fmaf(p, t, 2.862000669e-04f);
+  p = fmaf(p, t, 3.786277615e-03f);
+  p = fmaf(p, t, 5.280982382e-02f);
+  p = fmaf(p, t, 1.907734496e-01f);
+  p = fmaf(p, t, 1.128379076e+00f);
+  float q = 3.823944817e-05f;
+  q = fmaf(q, t, 1.169261335e-03f);
+  q = fmaf(q, t, 1.500781038e-02f);
+  q = fmaf(q, t, 1.142729919e-01f);
+  q = fmaf(q, t, 5.024007393e-01f);
+  q = fmaf(q, t, 1.0f);
+  return __fdividef(x * p, q);
+}
+// exact-form (erf) GELU and its derivative, fp32 (nn.GELU, F:55)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * exp2f(-0.72134752044448170f * x * x);
+  return fmaf(x, pdf, cdf);
 }
 
 // ------------------------------------------------------------------------------------------------

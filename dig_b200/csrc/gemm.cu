@@ -3,9 +3,10 @@
 //   out[M,N] = epilogue( alpha * A[M,K] . B[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
 //
 // One CTA per SM walks output tiles of 128 x BN.  Warp 0 feeds a ring of shared-memory stages with TMA
-// (128-byte swizzle), warp 1 issues tcgen05.mma from one thread and owns the TMEM allocation, warps 2..5
-// drain the double-buffered TMEM accumulator (one output row per thread) and apply the fused epilogue, so
-// tile i's epilogue overlaps tile i+1's MMAs.  Either operand may be K-major or MN-major (see
+// (128-byte swizzle), warp 1 issues tcgen05.mma from one thread and owns the TMEM allocation, warps 2..9
+// drain the double-buffered TMEM accumulator (tcgen05.ld, one row per thread), transpose 32x32 chunks through
+// per-warp shared memory and apply the fused epilogue with fully coalesced 128-bit global accesses, so tile i's
+// epilogue overlaps tile i+1's MMAs.  Either operand may be K-major or MN-major (see
 // include/dig_b200.h), which covers forward (x.W^T), dgrad (dy.W) and wgrad (dy^T.x) without any transposed
 // copies.  Replaces the cuBLAS calls behind F.linear in the reference (modeling_finetune.py:93,119,54,58;
 // modeling_pretrain_moco_mim_ori.py:463-482,422-426) and their autograd counterparts.
@@ -16,7 +17,8 @@ namespace dig {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kGemmThreads = 192;
+static constexpr int kEpiWarps = 8;
+static constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 
 struct GemmEpilogue {
   void* out;
@@ -33,6 +35,7 @@ struct GemmEpilogue {
   long long ldaux;
   float alpha;
   int atomic;
+  float* colsum;
 };
 
 template <int BN>
@@ -40,26 +43,41 @@ struct GemmSmem {
   static constexpr int kStageA = BM * BK * 2;
   static constexpr int kStageB = BN * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
-  static constexpr int kBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStages = (BN == 128) ? 5 : 6;
+  static constexpr int kEpi = kEpiWarps * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int kColsum = 2048 * 4;               // per-CTA column-sum scratch (N <= 2048 when colsum is requested)
+  static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+}
+
+// MODE: DIG_EPI_* or kEpiAtomic (split-K fp32 accumulate); OUT_F32: output element type.
+static constexpr int kEpiAtomic = 4;
+
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmEpilogue ep, int M,
                   int N, int K, int split_k, int kb_per_split) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
-  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStage);
-  uint64_t* full_bar = bars;                   // [kStages]  TMA -> MMA
-  uint64_t* empty_bar = bars + kStages;        // [kStages]  MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * kStages;    // [2]        MMA -> epilogue
-  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]     epilogue -> MMA
+  float* epi_smem = reinterpret_cast<float*>(smem + kStages * S::kStage);
+  float* cta_colsum = reinterpret_cast<float*>(smem + kStages * S::kStage + S::kEpi);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStage + S::kEpi + S::kColsum);
+  uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]        epilogue -> MMA
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -79,11 +97,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, kTmemCols);
+  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)
+    for (int i = threadIdx.x; i < N; i += kGemmThreads) cta_colsum[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -154,8 +174,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM -> registers -> global) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue: 8 warps; TMEM -> regs -> per-warp smem transpose -> coalesced fused epilogue ==========
+    // warp ew: TMEM lane quarter (warp & 3), column half (ew >> 2).  After the transpose lane l owns 4 consecutive columns
+    // (l & 7) of rows (l >> 3) + 4*i, so bias is one float4 per chunk and every global access covers whole 128-byte rows.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    float* tile = epi_smem + ew * 1024;
+    const int col4 = lane & 7, rsub = lane >> 3;
+    float* const out_f = reinterpret_cast<float*>(ep.out);
+    __nv_bfloat16* const out_h = reinterpret_cast<__nv_bfloat16*>(ep.out);
+    __nv_bfloat16* const aux = reinterpret_cast<__nv_bfloat16*>(ep.aux);
+    const long long ldo = ep.ldo, ldaux = ep.ldaux, ldr = ep.ldr, res_row_mod = ep.res_row_mod;
+    const float* const bias = ep.bias;
+    const float* const residual = ep.residual;
+    const uint8_t* const row_mask = ep.row_mask;
+    float* const colsum = ep.colsum;
+    const float alpha = ep.alpha;
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int n_blk = w % num_n;
@@ -164,131 +199,111 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const long long row = (long long)m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = row < M;
-      const bool masked = row_ok && ep.row_mask != nullptr && ep.row_mask[row] != 0;
-      const float* res_row = nullptr;
-      if (ep.residual != nullptr && row_ok)
-        res_row = ep.residual + (ep.res_row_mod > 0 ? (row % ep.res_row_mod) : row) * ep.ldr;
+      const long long row_base = (long long)m_blk * BM + quarter * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int cc = 0; cc < BN / 2; cc += 32) {
+        const int c = half * (BN / 2) + cc;
+        const int gcol = n_blk * BN + c + col4 * 4;
+        const bool col_ok = gcol < N;
+        const int rows_left = (int)min((long long)32, (long long)M - row_base);
+        float4 pre[8];   // residual rows (LINEAR) or aux rows (GELU_BWD / RELU_MASK) of this lane's 8 output positions
+        bool masked[8];
+        if (MODE == DIG_EPI_LINEAR) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            masked[i] = false;
+            if (col_ok && r < rows_left) {
+              const long long grow = row_base + r;
+              if (residual != nullptr) pre[i] = *reinterpret_cast<const float4*>(residual + (res_row_mod > 0 ? (grow % res_row_mod) : grow) * ldr + gcol);
+              if (row_mask != nullptr) masked[i] = row_mask[grow] != 0;
+            }
+          }
+        } else if (MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_RELU_MASK) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && r < rows_left) pre[i] = ld_bf16x4(aux + (row_base + r) * ldaux + gcol);
+          }
+        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c, v);
         tmem_ld_wait();
-        const int col0 = n_blk * BN + c;
-        if (row_ok && col0 < N) {
-          const bool full = (col0 + 32 <= N);
-          float f[32];
+        if (cc + 32 >= BN / 2) {  // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
-          if (ep.atomic) {
-            float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col0;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (MODE != kEpiAtomic && bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol));
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || col0 + j < N) atomicAdd(o + j, f[j]);
-            continue;
-          }
-          if (ep.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || col0 + j < N) f[j] += __ldg(ep.bias + col0 + j);
-          }
-          if (ep.mode == DIG_EPI_GELU) {
-            __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(ep.aux) + row * ep.ldaux + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 p;
-                p.x = pack_bf16(f[j + 0], f[j + 1]);
-                p.y = pack_bf16(f[j + 2], f[j + 3]);
-                p.z = pack_bf16(f[j + 4], f[j + 5]);
-                p.w = pack_bf16(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(a + j) = p;
-              }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < N; ++j) a[j] = __float2bfloat16(f[j]);
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            if (r >= rows_left) continue;
+            const long long grow = row_base + r;
+            float4 f = *reinterpret_cast<const float4*>(tile + r * 32 + ((col4 ^ (r & 7)) << 2));
+            f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha;
+            if (MODE == kEpiAtomic) {
+              float* o = out_f + grow * ldo + gcol;
+              atomicAdd(o, f.x); atomicAdd(o + 1, f.y); atomicAdd(o + 2, f.z); atomicAdd(o + 3, f.w);
+              continue;
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          } else if (ep.mode == DIG_EPI_GELU_BWD || ep.mode == DIG_EPI_RELU_MASK) {
-            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + row * ep.ldaux + col0;
-            float x[32];
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 p = *reinterpret_cast<const uint4*>(a + j);
-                x[j + 0] = bf16_lo(p.x); x[j + 1] = bf16_hi(p.x);
-                x[j + 2] = bf16_lo(p.y); x[j + 3] = bf16_hi(p.y);
-                x[j + 4] = bf16_lo(p.z); x[j + 5] = bf16_hi(p.z);
-                x[j + 6] = bf16_lo(p.w); x[j + 7] = bf16_hi(p.w);
-              }
-            } else {
-              for (int j = 0; j < 32; ++j) x[j] = (col0 + j < N) ? __bfloat162float(a[j]) : 0.f;
+            f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+            if (MODE == DIG_EPI_GELU) {
+              st_bf16x4(aux + grow * ldaux + gcol, f);
+              f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w);
+            } else if (MODE == DIG_EPI_GELU_BWD) {
+              const float4 x = pre[i];
+              f.x *= gelu_erf_grad(x.x); f.y *= gelu_erf_grad(x.y); f.z *= gelu_erf_grad(x.z); f.w *= gelu_erf_grad(x.w);
+            } else if (MODE == DIG_EPI_RELU_MASK) {
+              const float4 x = pre[i];
+              f.x = x.x > 0.f ? f.x : 0.f; f.y = x.y > 0.f ? f.y : 0.f; f.z = x.z > 0.f ? f.z : 0.f; f.w = x.w > 0.f ? f.w : 0.f;
             }
-            if (ep.mode == DIG_EPI_GELU_BWD) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(x[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = x[j] > 0.f ? f[j] : 0.f;
+            if (MODE == DIG_EPI_LINEAR) {
+              if (masked[i]) f = __ldg(reinterpret_cast<const float4*>(ep.row_mask_value + gcol));
+              f.x += pre[i].x; f.y += pre[i].y; f.z += pre[i].z; f.w += pre[i].w;
             }
-          }
-          if (masked) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || col0 + j < N) f[j] = __ldg(ep.row_mask_value + col0 + j);
-          }
-          if (res_row != nullptr) {
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
-                f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-              }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < N; ++j) f[j] += res_row[col0 + j];
-            }
-          }
-          if (ep.out_fp32) {
-            float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 32 && col0 + j < N; ++j) o[j] = f[j];
-            }
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + row * ep.ldo + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 p;
-                p.x = pack_bf16(f[j + 0], f[j + 1]);
-                p.y = pack_bf16(f[j + 2], f[j + 3]);
-                p.z = pack_bf16(f[j + 4], f[j + 5]);
-                p.w = pack_bf16(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = p;
-              }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < N; ++j) o[j] = __float2bfloat16(f[j]);
-            }
+            if (MODE == DIG_EPI_GELU_BWD) { cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w; }
+            if (OUT_F32) *reinterpret_cast<float4*>(out_f + grow * ldo + gcol) = f;
+            else st_bf16x4(out_h + grow * ldo + gcol, f);
           }
         }
+        if (MODE == DIG_EPI_GELU_BWD && colsum != nullptr) {  // column sums of the written tile: bias gradient of fc1
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+          }
+          if (col_ok && rsub == 0) {
+            atomicAdd(cta_colsum + gcol, cs.x); atomicAdd(cta_colsum + gcol + 1, cs.y);
+            atomicAdd(cta_colsum + gcol + 2, cs.z); atomicAdd(cta_colsum + gcol + 3, cs.w);
+          }
+        }
+        __syncwarp();
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)  // one global atomic per column per CTA
+    for (int i = threadIdx.x; i < N; i += kGemmThreads) atomicAdd(ep.colsum + i, cta_colsum[i]);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
 static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   CUtensorMap ta, tb;
@@ -312,8 +327,10 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
   ep.mode = g->epilogue; ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.atomic = g->split_k > 1 ? 1 : 0;
+  ep.colsum = g->colsum;
+  if (g->colsum) DIG_REQUIRE(g->epilogue == DIG_EPI_GELU_BWD && g->N <= 2048, "dig_gemm: colsum is built for DIG_EPI_GELU_BWD with N <= 2048 only");
 
-  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32>;
   static bool attr_set = false;
   if (!attr_set) {
     DIG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
@@ -326,12 +343,33 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   return 0;
 }
 
+// Instantiated (operand majors x epilogue x output type) combinations -- the ones the pre-training step uses, plus plain
+// LINEAR for every major combination.  Anything else is rejected with an error instead of a slow generic path.
 template <int BN>
-static int dispatch_major(const dig_gemm_t* g, cudaStream_t s) {
-  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm<BN, false, false>(g, s);
-  if (!g->a_mn_major && g->b_mn_major) return launch_gemm<BN, false, true>(g, s);
-  if (g->a_mn_major && !g->b_mn_major) return launch_gemm<BN, true, false>(g, s);
-  return launch_gemm<BN, true, true>(g, s);
+static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
+  const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0, f32 = g->out_fp32 != 0;
+  const int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+#define DIG_CASE(A, B, MODE, F32) \
+  if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm<BN, A, B, MODE, F32>(g, s);
+  DIG_CASE(false, false, DIG_EPI_LINEAR, false)   // forward Linear -> bf16 (qkv, pix_decoder)
+  DIG_CASE(false, false, DIG_EPI_LINEAR, true)    // forward Linear -> fp32 (+bias +residual, patch embed, BN-MLP heads)
+  DIG_CASE(false, false, DIG_EPI_GELU, false)     // fc1 + GELU
+  DIG_CASE(false, true, DIG_EPI_LINEAR, false)    // dgrad -> bf16
+  DIG_CASE(false, true, DIG_EPI_LINEAR, true)     // dgrad -> fp32
+  DIG_CASE(false, true, DIG_EPI_GELU_BWD, false)  // fc2 dgrad * gelu'
+  DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)  // BN-MLP dgrad through ReLU
+  DIG_CASE(true, true, DIG_EPI_LINEAR, true)      // wgrad, single pass
+  DIG_CASE(true, true, kEpiAtomic, true)          // wgrad, split-K
+  DIG_CASE(true, true, DIG_EPI_LINEAR, false)
+  DIG_CASE(true, false, DIG_EPI_LINEAR, true)
+  DIG_CASE(true, false, DIG_EPI_LINEAR, false)
+  DIG_CASE(false, false, kEpiAtomic, true)
+  DIG_CASE(false, true, kEpiAtomic, true)
+  DIG_CASE(true, false, kEpiAtomic, true)
+#undef DIG_CASE
+  set_last_error("dig_gemm: combination not built (a_mn=%d b_mn=%d epilogue=%d split_k=%d out_fp32=%d)", (int)amn, (int)bmn, g->epilogue,
+                 g->split_k, (int)f32);
+  return -1;
 }
 
 }  // namespace dig
@@ -346,13 +384,14 @@ extern "C" int dig_gemm(const dig_gemm_t* g, void* stream) {
               (long long)g->lda, (long long)g->ldb);
   DIG_REQUIRE(((uintptr_t)g->A & 15) == 0 && ((uintptr_t)g->B & 15) == 0 && ((uintptr_t)g->out & 15) == 0,
               "dig_gemm: operands must be 16-byte aligned");
-  DIG_REQUIRE(g->ldo % 8 == 0, "dig_gemm: ldo must be a multiple of 8");
+  DIG_REQUIRE(g->ldo % 4 == 0 && g->N % 4 == 0, "dig_gemm: N and ldo must be multiples of 4 (N=%lld ldo=%lld)", (long long)g->N, (long long)g->ldo);
+  DIG_REQUIRE(!g->residual || g->ldr % 4 == 0, "dig_gemm: ldr must be a multiple of 4");
   if (g->split_k > 1)
-    DIG_REQUIRE(g->out_fp32 && g->epilogue == DIG_EPI_LINEAR && !g->bias && !g->residual && !g->row_mask,
+    DIG_REQUIRE(g->out_fp32 && g->epilogue == DIG_EPI_LINEAR && !g->bias && !g->residual && !g->row_mask && !g->colsum,
                 "dig_gemm: split_k>1 needs a plain fp32 accumulate epilogue");
-  if (g->epilogue != DIG_EPI_LINEAR) DIG_REQUIRE(g->aux != nullptr && g->ldaux % 8 == 0, "dig_gemm: epilogue %d needs aux", g->epilogue);
+  if (g->epilogue != DIG_EPI_LINEAR) DIG_REQUIRE(g->aux != nullptr && g->ldaux % 4 == 0, "dig_gemm: epilogue %d needs aux", g->epilogue);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // tile width: 128 wherever N fills it, 64 for the narrow heads (pix_decoder 192/48)
-  if (g->N % 128 == 0 || g->N > 256) return dispatch_major<128>(g, s);
-  return dispatch_major<64>(g, s);
+  if (g->N % 128 == 0 || g->N > 256) return dispatch<128>(g, s);
+  return dispatch<64>(g, s);
 }

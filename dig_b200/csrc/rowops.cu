@@ -75,21 +75,112 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
-// dx = dres + LN_bwd(dy);  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy  (dy is w.r.t. the LN (or GELU(LN)) output)
-template <bool GELU>
+// dx = dres + LN_bwd(dy);  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy;  dxsum += sum_rows dx
+// (dy is w.r.t. the LN output, or the GELU(LN) output when GELU).  One warp per row, D/32 contiguous-by-4 columns per lane,
+// every global access 128-bit (64-bit for the bf16 streams); all loads of a row are issued before the first reduction.
+template <int D, bool GELU>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* dres, float* dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int d) {
-  extern __shared__ float part[];  // [2][d] block partials
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows) {
+  constexpr int NV = D / 128;  // float4 groups per lane
+  __shared__ float part[3 * D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  float4 ag[NV], ab[NV], ax[NV], gm[NV], bt[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    ag[k] = ab[k] = ax[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[k] = *reinterpret_cast<const float4*>(gamma + k * 128 + lane * 4);
+    bt[k] = GELU ? *reinterpret_cast<const float4*>(beta + k * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row = (long long)blockIdx.x * nwarps + warp; row < rows; row += (long long)gridDim.x * nwarps) {
+    float4 xv[NV], dv[NV], rv[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = k * 128 + lane * 4;
+      xv[k] = *reinterpret_cast<const float4*>(x + row * D + c);
+      const uint2 t = *reinterpret_cast<const uint2*>(dy + row * D + c);
+      dv[k] = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
+      rv[k] = dres ? *reinterpret_cast<const float4*>(dres + row * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float* xe = reinterpret_cast<float*>(&xv[k]);
+      float* de = reinterpret_cast<float*>(&dv[k]);
+      const float* ge = reinterpret_cast<const float*>(&gm[k]);
+      const float* be = reinterpret_cast<const float*>(&bt[k]);
+      float* age = reinterpret_cast<float*>(&ag[k]);
+      float* abe = reinterpret_cast<float*>(&ab[k]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = (xe[e] - mu) * rs;
+        float d0 = de[e];
+        if (GELU) d0 *= gelu_erf_grad(xh * ge[e] + be[e]);
+        age[e] += d0 * xh;
+        abe[e] += d0;
+        const float g = d0 * ge[e];
+        c1 += g;
+        c2 += g * xh;
+        xe[e] = xh;   // keep xhat
+        de[e] = g;    // keep dy*gamma
+      }
+    }
+    c1 = warp_sum(c1) * (1.0f / D);
+    c2 = warp_sum(c2) * (1.0f / D);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = k * 128 + lane * 4;
+      float4 o;
+      o.x = rs * (dv[k].x - c1 - xv[k].x * c2) + rv[k].x;
+      o.y = rs * (dv[k].y - c1 - xv[k].y * c2) + rv[k].y;
+      o.z = rs * (dv[k].z - c1 - xv[k].z * c2) + rv[k].z;
+      o.w = rs * (dv[k].w - c1 - xv[k].w * c2) + rv[k].w;
+      ax[k].x += o.x; ax[k].y += o.y; ax[k].z += o.z; ax[k].w += o.w;
+      if (dx_f32) *reinterpret_cast<float4*>(dx_f32 + row * D + c) = o;
+      if (dx_bf16) *reinterpret_cast<uint2*>(dx_bf16 + row * D + c) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = k * 128 + lane * 4;
+    const float* age = reinterpret_cast<const float*>(&ag[k]);
+    const float* abe = reinterpret_cast<const float*>(&ab[k]);
+    const float* axe = reinterpret_cast<const float*>(&ax[k]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(&part[c + e], age[e]);
+      atomicAdd(&part[D + c + e], abe[e]);
+      if (dxsum) atomicAdd(&part[2 * D + c + e], axe[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, part[i]);
+    atomicAdd(dbeta + i, part[D + i]);
+    if (dxsum) atomicAdd(dxsum + i, part[2 * D + i]);
+  }
+}
+
+// generic-width variant (d % 64 == 0, d <= 512), used for the 192-wide pix_decoder LayerNorm
+template <bool GELU>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                             const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             const float* dres, float* dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
+                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int d) {
+  extern __shared__ float part[];  // [3][d] block partials (dgamma | dbeta | column sums of dx)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int np = d >> 6;
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) part[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) part[i] = 0.f;
   __syncthreads();
-  float2 ag[kLnMaxPairs], ab[kLnMaxPairs];
+  float2 ag[kLnMaxPairs], ab[kLnMaxPairs], ax[kLnMaxPairs];
 #pragma unroll
-  for (int k = 0; k < kLnMaxPairs; ++k) { ag[k] = make_float2(0.f, 0.f); ab[k] = make_float2(0.f, 0.f); }
+  for (int k = 0; k < kLnMaxPairs; ++k) { ag[k] = make_float2(0.f, 0.f); ab[k] = make_float2(0.f, 0.f); ax[k] = make_float2(0.f, 0.f); }
   float2 gm[kLnMaxPairs], bt[kLnMaxPairs];
 #pragma unroll
   for (int k = 0; k < kLnMaxPairs; ++k)
@@ -131,6 +222,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
           const float2 r = *reinterpret_cast<const float2*>(dres + row * d + c);
           o0 += r.x; o1 += r.y;
         }
+        ax[k].x += o0; ax[k].y += o1;
         if (dx_f32) *reinterpret_cast<float2*>(dx_f32 + row * d + c) = make_float2(o0, o1);
         if (dx_bf16) *reinterpret_cast<uint32_t*>(dx_bf16 + row * d + c) = pack_bf16(o0, o1);
       }
@@ -141,11 +233,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
       const int c = k * 64 + lane * 2;
       atomicAdd(&part[c], ag[k].x); atomicAdd(&part[c + 1], ag[k].y);
       atomicAdd(&part[d + c], ab[k].x); atomicAdd(&part[d + c + 1], ab[k].y);
+      if (dxsum) { atomicAdd(&part[2 * d + c], ax[k].x); atomicAdd(&part[2 * d + c + 1], ax[k].y); }
     }
   __syncthreads();
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     atomicAdd(dgamma + i, part[i]);
     atomicAdd(dbeta + i, part[d + i]);
+    if (dxsum) atomicAdd(dxsum + i, part[2 * d + i]);
   }
 }
 
@@ -228,38 +322,62 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int
 // ------------------------------------------------------------------------------------------------
 // column sums: out[n] += sum_m x[m, n]   (bias gradients).  Block = 32 column lanes x 8 row lanes.
 // ------------------------------------------------------------------------------------------------
+// Each thread owns VEC consecutive columns (one 128-bit load per row), a warp covers 32*VEC columns of a row.
 template <typename T>
-__device__ __forceinline__ float ld_as_float(const T* p);
+struct ColVec;
 template <>
-__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+struct ColVec<float> {
+  static constexpr int kVec = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
 template <>
-__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+struct ColVec<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+    v[4] = bf16_lo(t.z); v[5] = bf16_hi(t.z); v[6] = bf16_lo(t.w); v[7] = bf16_hi(t.w);
+  }
+};
 
 template <typename T, bool SQUARES>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, float* __restrict__ out_sq, long long rows, int cols,
               int rows_per_block) {
-  __shared__ float sm[2][8][33];
+  constexpr int V = ColVec<T>::kVec;
+  __shared__ float sm[SQUARES ? 2 : 1][8][32 * V + 1];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + cx;
+  const int col = (blockIdx.x * 32 + cx) * V;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-  float s = 0.f, q = 0.f;
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
   if (col < cols)
     for (long long r = r0 + ry; r < r1; r += 8) {
-      const float v = ld_as_float<T>(x + r * ld + col);
-      s += v;
-      if (SQUARES) q += v * v;
-    }
-  sm[0][ry][cx] = s;
-  sm[1][ry][cx] = q;
-  __syncthreads();
-  if (ry == 0 && col < cols) {
-    float ts = 0.f, tq = 0.f;
+      float v[V];
+      ColVec<T>::load(x + r * ld + col, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { ts += sm[0][k][cx]; tq += sm[1][k][cx]; }
-    atomicAdd(out + col, ts);
-    if (SQUARES) atomicAdd(out_sq + col, tq);
+      for (int k = 0; k < V; ++k) { s[k] += v[k]; if (SQUARES) q[k] += v[k] * v[k]; }
+    }
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    sm[0][ry][cx * V + k] = s[k];
+    if (SQUARES) sm[SQUARES ? 1 : 0][ry][cx * V + k] = q[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * V; c += 256) {
+    const int gc = blockIdx.x * 32 * V + c;
+    if (gc < cols) {
+      float ts = 0.f, tq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { ts += sm[0][k][c]; if (SQUARES) tq += sm[SQUARES ? 1 : 0][k][c]; }
+      atomicAdd(out + gc, ts);
+      if (SQUARES) atomicAdd(out_sq + gc, tq);
+    }
   }
 }
 
@@ -429,19 +547,24 @@ extern "C" int dig_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int dig_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                                 int64_t rows, int32_t d, int32_t gelu, void* stream) {
+                                 float* dxsum, int64_t rows, int32_t d, int32_t gelu, void* stream) {
   DIG_REQUIRE(dy && x && mean && rstd && gamma && dgamma && dbeta && rows > 0, "dig_layernorm_bwd: bad arguments");
   DIG_REQUIRE(d % 64 == 0 && d <= 512, "dig_layernorm_bwd: d must be a multiple of 64 and <= 512 (got %d)", d);
   DIG_REQUIRE(!gelu || beta, "dig_layernorm_bwd: gelu variant needs beta");
   int grid = num_sms() * 4;
   if (grid > blocks_for(rows, 8)) grid = blocks_for(rows, 8);
-  const size_t sm = 2 * d * sizeof(float);
-  if (gelu)
-    layernorm_bwd_kernel<true><<<grid, 256, sm, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, x, mean, rstd, gamma, beta, dres, dx_f32,
-                                                                      (__nv_bfloat16*)dx_bf16, dgamma, dbeta, rows, d);
-  else
-    layernorm_bwd_kernel<false><<<grid, 256, sm, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, x, mean, rstd, gamma, beta, dres, dx_f32,
-                                                                       (__nv_bfloat16*)dx_bf16, dgamma, dbeta, rows, d);
+  cudaStream_t s = (cudaStream_t)stream;
+  const __nv_bfloat16* dyh = (const __nv_bfloat16*)dy;
+  __nv_bfloat16* dxh = (__nv_bfloat16*)dx_bf16;
+  if (!gelu && d == 384) {
+    layernorm_bwd_kernel<384, false><<<grid, 256, 0, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows);
+  } else if (!gelu && d == 512) {
+    layernorm_bwd_kernel<512, false><<<grid, 256, 0, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows);
+  } else {
+    const size_t sm = 3 * d * sizeof(float);
+    if (gelu) layernorm_bwd_generic_kernel<true><<<grid, 256, sm, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows, d);
+    else layernorm_bwd_generic_kernel<false><<<grid, 256, sm, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows, d);
+  }
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -486,8 +609,11 @@ extern "C" int dig_scatter_add_rows(const float* src, const int32_t* idx, float*
 extern "C" int dig_colsum(const void* x, int32_t x_is_fp32, int64_t ld, float* out, float* out_sq, int64_t rows, int32_t cols,
                           void* stream) {
   DIG_REQUIRE(x && out && rows > 0 && cols > 0, "dig_colsum: bad arguments");
-  const int gx = (cols + 31) / 32;
-  int gy = (num_sms() * 8 + gx - 1) / gx;
+  const int vec = x_is_fp32 ? 4 : 8;
+  DIG_REQUIRE(cols % vec == 0 && ld % vec == 0 && ((uintptr_t)x & 15) == 0, "dig_colsum: cols/ld must be multiples of %d and x 16-byte aligned",
+              vec);
+  const int gx = (cols + 32 * vec - 1) / (32 * vec);
+  int gy = (num_sms() * 4 + gx - 1) / gx;
   if (gy > (rows + 63) / 64) gy = (int)((rows + 63) / 64);
   if (gy < 1) gy = 1;
   const int rpb = (int)((rows + gy - 1) / gy);

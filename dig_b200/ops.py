@@ -35,6 +35,7 @@ class _Gemm(ctypes.Structure):
         ("aux", ctypes.c_void_p), ("ldaux", ctypes.c_int64),
         ("alpha", ctypes.c_float),
         ("split_k", ctypes.c_int32),
+        ("colsum", ctypes.c_void_p),
     ]
 
 
@@ -144,7 +145,7 @@ def _req(t, dtype, name):
 
 
 def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=None, res_row_mod=0, row_mask=None,
-         row_mask_value=None, epilogue=EPI_LINEAR, aux=None, alpha=1.0, split_k=1):
+         row_mask_value=None, epilogue=EPI_LINEAR, aux=None, alpha=1.0, split_k=1, colsum=None):
     """out[M,N] = epilogue(alpha * A.B^T) on tcgen05 (see include/dig_b200.h).
 
     a: bf16 [M,K] (K-major) or [K,M] (a_mn_major); b: bf16 [N,K] or [K,N] (b_mn_major);
@@ -184,6 +185,9 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
         g.aux, g.ldaux = aux.data_ptr(), aux.stride(0)
     g.alpha = alpha
     g.split_k = split_k
+    if colsum is not None:
+        _req(colsum, torch.float32, "colsum")
+        g.colsum = colsum.data_ptr()
     if _gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -249,20 +249,20 @@ class PretrainStep:
         dat = B.get("bw.dat", (M, d), BF16)
         dqkv = B.get("bw.dqkv", (M, 3 * d), BF16)
         dqkvb = B.get("bw.dqkvb", (3 * d,), F32)
+        # fc2 bias gradient of the last block = column sums of the incoming gradient; for the other blocks it falls out of
+        # the LayerNorm-1 backward of the block above (dxsum), like the proj bias gradient out of the LayerNorm-2 backward.
+        call("dig_colsum", gb, 0, d, grads[W["blocks"][-1]["name"] + "mlp.fc2.bias"], None, M, d)
         for l in reversed(range(self.depth)):
             bw, a = W["blocks"][l], sv["acts"][l]
             nm = bw["name"]
             # ---- MLP (F:53-60) ----
-            call("dig_colsum", gb, 0, d, grads[nm + "mlp.fc2.bias"], None, M, d)
             ops.gemm(gb, a["hpost"], grads[nm + "mlp.fc2.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(d, 4 * d, M))
-            ops.gemm(gb, bw["f2w"], dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=a["hpre"])
-            call("dig_colsum", dh, 0, 4 * d, grads[nm + "mlp.fc1.bias"], None, M, 4 * d)
+            ops.gemm(gb, bw["f2w"], dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=a["hpre"], colsum=grads[nm + "mlp.fc1.bias"])
             ops.gemm(dh, a["ln2"], grads[nm + "mlp.fc1.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(4 * d, d, M))
             ops.gemm(dh, bw["f1w"], dln, b_mn_major=True)
             call("dig_layernorm_bwd", dln, a["xm"], a["mean2"], a["rstd2"], bw["n2w"], None, g, g, gb,
-                 grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], M, d, 0)
+                 grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], grads[nm + "attn.proj.bias"], M, d, 0)
             # ---- attention (F:87-125) ----
-            call("dig_colsum", gb, 0, d, grads[nm + "attn.proj.bias"], None, M, d)
             ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(d, d, M))
             ops.gemm(gb, bw["pw"], dat, b_mn_major=True)
             ops.attention_bwd(a["qkv"], a["att"], dat, a["lse"], dqkv, h, self.scale)
@@ -272,8 +272,9 @@ class PretrainStep:
             grads[nm + "attn.v_bias"].copy_(dqkvb[2 * d:])
             ops.gemm(dqkv, a["ln1"], grads[nm + "attn.qkv.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(3 * d, d, M))
             ops.gemm(dqkv, bw["qkvw"], dln, b_mn_major=True)
+            prev_b2 = grads[W["blocks"][l - 1]["name"] + "mlp.fc2.bias"] if l > 0 else None
             call("dig_layernorm_bwd", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], None, g, g, gb,
-                 grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], M, d, 0)
+                 grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], prev_b2, M, d, 0)
         # ---- patch embed + mask token (F:190-196, V:95-99); pos_embed carries no gradient (V:99 detach) ----
         pre = W["pre"]
         gz = B.get("bw.gz", (M, d), BF16)
@@ -510,7 +511,7 @@ class PretrainStep:
             dt2 = Bf.get("bw.dt2", (n_m, 192), BF16)
             ln = model.pix_decoder[2]
             call("dig_layernorm_bwd", dt3, sv["t2"], sv["dmean"], sv["drstd"], ln.weight, ln.bias, None, None, dt2,
-                 grads["pix_decoder.2.weight"], grads["pix_decoder.2.bias"], n_m, 192, 1)
+                 grads["pix_decoder.2.weight"], grads["pix_decoder.2.bias"], None, n_m, 192, 1)
             ops.gemm(dt2, sv["t1"], grads["pix_decoder.1.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(192, 192, n_m, 64))
             dt1 = Bf.get("bw.dt1", (n_m, 192), BF16)
             ops.gemm(dt2, S_["pix_decoder.1.weight"], dt1, b_mn_major=True)

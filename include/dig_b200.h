@@ -50,6 +50,8 @@ typedef struct dig_gemm {
   float alpha;
   int32_t split_k;                                 /* >1: K is split over CTAs, fp32 atomicAdd into out (out_fp32 must be 1,
                                                       DIG_EPI_LINEAR without bias/residual); out must be pre-initialised */
+  float* colsum;                                   /* optional fp32 [N]: colsum[n] += sum_m out[m,n] (bias gradient of the layer
+                                                      that produced the GEMM input), NULL to skip                        */
 } dig_gemm_t;
 int dig_gemm(const dig_gemm_t* g, void* stream);
 
@@ -73,11 +75,12 @@ int dig_im2col_patch4(const float* images, void* out, int64_t num_images, void* 
  * mean/rstd fp32 [rows] are saved for the backward (may be NULL).  d % 64 == 0, d <= 512.            */
 int dig_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                       int64_t rows, int32_t d, float eps, int32_t gelu, void* stream);
-/* LayerNorm backward: dx = dres + dLN(dy) written as fp32 and/or bf16 (either may be NULL), dgamma/dbeta
- * accumulated (+=).  dy is bf16, w.r.t. the LN output (or the GELU(LN) output when gelu != 0).       */
+/* LayerNorm backward: dx = dres + dLN(dy) written as fp32 and/or bf16 (either may be NULL, dx_f32 may alias dres),
+ * dgamma/dbeta accumulated (+=); dxsum (optional fp32 [d]) += column sums of dx, i.e. the bias gradient of the
+ * Linear that produced the residual branch.  dy is bf16, w.r.t. the LN output (or GELU(LN) output when gelu != 0). */
 int dig_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* beta, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                      int64_t rows, int32_t d, int32_t gelu, void* stream);
+                      float* dxsum, int64_t rows, int32_t d, int32_t gelu, void* stream);
 /* PatchNet pooling without patch transformer (M:189-193): [S,8,32,d] fp32 -> mean over 8 x (32/num_windows)
  * token windows -> bf16 [S*num_windows, d].  Sequences < split come from x0, the others from x1.     */
 int dig_pool_fwd(const float* x0, const float* x1, int64_t split, void* out, int64_t num_seqs, int32_t d,

@@ -53,9 +53,12 @@ aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16); outb = torch.empty(M,
 ops.gemm(a, b, outb, bias=bias, epilogue=ops.EPI_GELU, aux=aux)
 pre = a.float() @ b.float().t() + bias
 print("gelu", (outb.float() - torch.nn.functional.gelu(pre)).abs().max().item(), "pre", (aux.float() - pre).abs().max().item())
-ops.gemm(a, b, out, epilogue=ops.EPI_GELU_BWD, aux=aux)
+bt = b.t().contiguous()
+cs = torch.zeros(N, device=dev)
+ops.gemm(a, bt, outb, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=aux, colsum=cs)
 x = aux.float().requires_grad_(True); torch.nn.functional.gelu(x).sum().backward()
-print("gelu_bwd", (out - (a.float() @ b.float().t()) * x.grad).abs().max().item())
+refb = (a.float() @ b.float().t()) * x.grad
+print("gelu_bwd", (outb.float() - refb).abs().max().item(), "colsum rel", ((cs - refb.sum(0)).abs().max() / refb.sum(0).abs().max()).item())
 mask = (torch.rand(M, device=dev) < 0.5).to(torch.uint8); mval = torch.randn(N, device=dev); pos = torch.randn(256, N, device=dev)
 ops.gemm(a, b, out, bias=bias, residual=pos, res_row_mod=256, row_mask=mask, row_mask_value=mval)
 r = torch.where(mask.bool()[:, None], mval[None, :].expand(M, N), a.float() @ b.float().t() + bias) + pos.repeat(M // 256, 1)
