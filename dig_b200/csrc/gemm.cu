@@ -197,37 +197,43 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int m_blk = (w / num_n) % num_m;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const long long row_base = (long long)m_blk * BM + quarter * 32;
+      const int rows_left = (int)min((long long)32, (long long)M - row_base);
+      // Operands the epilogue reads from HBM (residual rows, or the bf16 aux rows) are requested for every chunk of this warp
+      // BEFORE waiting for the accumulator, so their latency hides behind the tile's MMAs.  Raw bits only: no use before the wait.
+      constexpr int NCH = BN / 64;
+      float4 pre[NCH][8];
+      uint32_t maskbits[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int gcol_p = n_blk * BN + half * (BN / 2) + ch * 32 + col4 * 4;
+        maskbits[ch] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rsub;
+          pre[ch][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gcol_p < N && r < rows_left) {
+            const long long grow = row_base + r;
+            if (MODE == DIG_EPI_LINEAR) {
+              if (residual != nullptr)
+                pre[ch][i] = *reinterpret_cast<const float4*>(residual + (res_row_mod > 0 ? (grow % res_row_mod) : grow) * ldr + gcol_p);
+              if (row_mask != nullptr && row_mask[grow] != 0) maskbits[ch] |= 1u << i;
+            } else if (MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_RELU_MASK) {
+              const uint2 t = *reinterpret_cast<const uint2*>(aux + grow * ldaux + gcol_p);
+              pre[ch][i].x = __uint_as_float(t.x);
+              pre[ch][i].y = __uint_as_float(t.y);
+            }
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const long long row_base = (long long)m_blk * BM + quarter * 32;
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 2; cc += 32) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int cc = ch * 32;
         const int c = half * (BN / 2) + cc;
         const int gcol = n_blk * BN + c + col4 * 4;
         const bool col_ok = gcol < N;
-        const int rows_left = (int)min((long long)32, (long long)M - row_base);
-        float4 pre[8];   // residual rows (LINEAR) or aux rows (GELU_BWD / RELU_MASK) of this lane's 8 output positions
-        bool masked[8];
-        if (MODE == DIG_EPI_LINEAR) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rsub;
-            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            masked[i] = false;
-            if (col_ok && r < rows_left) {
-              const long long grow = row_base + r;
-              if (residual != nullptr) pre[i] = *reinterpret_cast<const float4*>(residual + (res_row_mod > 0 ? (grow % res_row_mod) : grow) * ldr + gcol);
-              if (row_mask != nullptr) masked[i] = row_mask[grow] != 0;
-            }
-          }
-        } else if (MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_RELU_MASK) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rsub;
-            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok && r < rows_left) pre[i] = ld_bf16x4(aux + (row_base + r) * ldaux + gcol);
-          }
-        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c, v);
         tmem_ld_wait();
@@ -262,15 +268,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
               st_bf16x4(aux + grow * ldaux + gcol, f);
               f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w);
             } else if (MODE == DIG_EPI_GELU_BWD) {
-              const float4 x = pre[i];
+              const uint32_t lo = __float_as_uint(pre[ch][i].x), hi = __float_as_uint(pre[ch][i].y);
+              const float4 x = make_float4(bf16_lo(lo), bf16_hi(lo), bf16_lo(hi), bf16_hi(hi));
               f.x *= gelu_erf_grad(x.x); f.y *= gelu_erf_grad(x.y); f.z *= gelu_erf_grad(x.z); f.w *= gelu_erf_grad(x.w);
             } else if (MODE == DIG_EPI_RELU_MASK) {
-              const float4 x = pre[i];
+              const uint32_t lo = __float_as_uint(pre[ch][i].x), hi = __float_as_uint(pre[ch][i].y);
+              const float4 x = make_float4(bf16_lo(lo), bf16_hi(lo), bf16_lo(hi), bf16_hi(hi));
               f.x = x.x > 0.f ? f.x : 0.f; f.y = x.y > 0.f ? f.y : 0.f; f.z = x.z > 0.f ? f.z : 0.f; f.w = x.w > 0.f ? f.w : 0.f;
             }
             if (MODE == DIG_EPI_LINEAR) {
-              if (masked[i]) f = __ldg(reinterpret_cast<const float4*>(ep.row_mask_value + gcol));
-              f.x += pre[i].x; f.y += pre[i].y; f.z += pre[i].z; f.w += pre[i].w;
+              if (maskbits[ch] & (1u << i)) f = __ldg(reinterpret_cast<const float4*>(ep.row_mask_value + gcol));
+              f.x += pre[ch][i].x; f.y += pre[ch][i].y; f.z += pre[ch][i].z; f.w += pre[ch][i].w;
             }
             if (MODE == DIG_EPI_GELU_BWD) { cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w; }
             if (OUT_F32) *reinterpret_cast<float4*>(out_f + grow * ldo + gcol) = f;

@@ -18,7 +18,7 @@ import math
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import dist_layout, ops
 from .ops import call
 
 F32, BF16 = torch.float32, torch.bfloat16
@@ -306,10 +306,7 @@ class PretrainStep:
             stats = B.get("%s.st%d" % (tag, li), (2 * C,), F32)
             stats.zero_()
             call("dig_colsum", z, 1, C, stats, stats[C:], rows, C)
-            count = float(rows)
-            if self._bn_sync(bn):
-                dist.all_reduce(stats)
-                count = float(rows * world)
+            count = dist_layout.sync_batch_stats(stats, rows) if self._bn_sync(bn) else float(rows)
             a_out = B.get("%s.a%d" % (tag, li), (rows, C), BF16) if (not last or want_bf16_out) else None
             out_f32 = B.get("%s.out" % tag, (rows, C), F32) if last else None
             gamma, beta = (bn.weight, bn.bias) if bn.affine else (None, None)
@@ -389,15 +386,7 @@ class PretrainStep:
         Q, C = R // 2, k.shape[1]
         kn = Bf.get("kn", (R, C), F32)
         call("dig_l2norm_fwd", k, kn, None, R, C)
-        if world > 1:                                                        # concat_all_gather, M:580-591
-            kall = Bf.get("kall", (world, R, C), F32)
-            dist.all_gather_into_tensor(kall, kn)
-            k1_all = Bf.get("k1all", (world * Q, C), F32)
-            k2_all = Bf.get("k2all", (world * Q, C), F32)
-            k1_all.view(world, Q, C).copy_(kall[:, :Q])
-            k2_all.view(world, Q, C).copy_(kall[:, Q:])
-        else:
-            k1_all, k2_all = kn[:Q], kn[Q:]
+        k1_all, k2_all = dist_layout.gather_keys(kn, Bf.get("kall", (world, R, C), F32) if world > 1 else None)  # M:580-591
 
         # ---- online branch ----
         W = self._enc_weights("encoder.")
@@ -424,8 +413,8 @@ class PretrainStep:
         lg2 = Bf.get("nce.lg2", (Q, Nk), F32)
         call("dig_sgemm_f32", qn[:Q], k2_all, lg1, Q, Nk, C, 1, 1.0 / self.T)
         call("dig_sgemm_f32", qn[Q:], k1_all, lg2, Q, Nk, C, 1, 1.0 / self.T)
-        call("dig_infonce_rows", lg1, Q, Nk, Q * rank, self.T, res[0])
-        call("dig_infonce_rows", lg2, Q, Nk, Q * rank, self.T, res[1])
+        call("dig_infonce_rows", lg1, Q, Nk, dist_layout.label_offset(Q, rank), self.T, res[0])
+        call("dig_infonce_rows", lg2, Q, Nk, dist_layout.label_offset(Q, rank), self.T, res[1])
 
         # ---- masked-pixel decoder on the masked rows of view 0 (M:561-570; row-wise, so gather first) ----
         n_per = self._masked_per_sample(vis_mask_pos)

@@ -93,24 +93,38 @@ def install_stubs():
     _mod("turtle", Turtle=_Turtle)
 
 
+_REF_CACHE = None
+_SHADOWED = ("modeling_finetune", "modeling_pretrain_vit", "modeling_pretrain_moco_mim_ori", "engine_for_pretraining_moco")
+
+
 def import_reference():
-    """Returns (modeling module M, engine module E, utils module U, custom_optim AdamW class)."""
+    """Returns (modeling module M, engine module E, utils module U, custom_optim AdamW class) of the REFERENCE.
+
+    The repo root holds drop-in modules with the reference's names (modeling_pretrain_moco_mim_ori.py,
+    engine_for_pretraining_moco.py); they are moved aside in sys.modules while the reference's own files are imported from
+    REFERENCE_ROOT and put back afterwards, so both can live in one process."""
+    global _REF_CACHE
+    if _REF_CACHE is not None:
+        return _REF_CACHE
     if not reference_available():
         raise RuntimeError("reference sources not found at %s" % REFERENCE_ROOT)
     install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    import modeling_pretrain_moco_mim_ori as M  # noqa
-    if not hasattr(M, "MoCo_ViT") or "dig_b200" in getattr(M, "__file__", ""):
-        # our own drop-in of the same name was imported first; load the reference's by path
-        import importlib.util
-        for name in ("modeling_finetune", "modeling_pretrain_vit", "modeling_pretrain_moco_mim_ori"):
-            sys.modules.pop(name, None)
+    saved = {n: sys.modules.pop(n) for n in _SHADOWED if n in sys.modules}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import importlib
         M = importlib.import_module("modeling_pretrain_moco_mim_ori")
-    import engine_for_pretraining_moco as E  # noqa
-    from utils import utils as U  # noqa
-    from custom_optim.adamw import AdamW  # noqa
-    return M, E, U, AdamW
+        E = importlib.import_module("engine_for_pretraining_moco")
+        U = importlib.import_module("utils.utils")
+        AdamW = importlib.import_module("custom_optim.adamw").AdamW
+        assert os.path.abspath(M.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), M.__file__
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for n in _SHADOWED:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved)
+    _REF_CACHE = (M, E, U, AdamW)
+    return _REF_CACHE
 
 
 def create_reference_model(name="pretrain_simmim_moco_ori_vit_small_patch4_32x128", seed=0, **over):

@@ -1,0 +1,106 @@
+"""Host-side logic of the engine (no GPU): schedules, meters, loss-weight warm-up, rank layout under a 2-process gloo group."""
+import math
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dig_b200 import utils
+
+
+def test_cosine_scheduler_matches_reference_formula():
+    s = utils.cosine_scheduler(1.0, 0.1, epochs=3, niter_per_ep=10, warmup_epochs=1, start_warmup_value=0.0)
+    assert len(s) == 30 and s[0] == 0.0 and s[9] == pytest.approx(1.0)
+    it = np.arange(20)
+    assert np.allclose(s[10:], 0.1 + 0.45 * (1 + np.cos(np.pi * it / 20)))
+    s2 = utils.cosine_scheduler(1.0, 0.1, epochs=3, niter_per_ep=10, warmup_epochs=0)
+    assert len(s2) == 30 and s2[0] == pytest.approx(1.0)
+    # reference quirk (utils.py:525-538): warmup_steps without warmup_epochs shortens the table and trips its own assert
+    with pytest.raises(AssertionError):
+        utils.cosine_scheduler(1.0, 0.1, epochs=3, niter_per_ep=10, warmup_epochs=0, warmup_steps=5)
+
+
+def test_moco_momentum_schedule():
+    a = types.SimpleNamespace(epochs=10, moco_m=0.99)
+    assert utils.adjust_moco_momentum(0, a) == pytest.approx(0.99)
+    assert utils.adjust_moco_momentum(10, a) == pytest.approx(1.0)
+    assert utils.adjust_moco_momentum(5, a) == pytest.approx(1 - 0.5 * (1 + math.cos(math.pi / 2)) * 0.01)
+
+
+def test_meters():
+    m = utils.SmoothedValue(window_size=3)
+    for v in (1.0, 2.0, 3.0, 10.0):
+        m.update(v)
+    assert m.global_avg == pytest.approx(4.0) and m.median == 3.0 and m.max == 10.0 and m.value == 10.0
+    ml = utils.MetricLogger()
+    ml.update(a=1.0, b=torch.tensor(2.0), c=None)
+    assert set(ml.meters) == {"a", "b"} and ml.b.global_avg == 2.0
+    out = list(ml.log_every(range(3), 100, "hdr"))
+    assert out == [0, 1, 2]
+
+
+def test_scaler_state_has_scale():
+    s = utils.NativeScalerWithGradNormCount()
+    assert s.state_dict()["scale"] == 1.0          # engine logs it (E:157)
+
+
+def test_engine_rejects_unbuilt_paths():
+    from dig_b200.engine import train_one_epoch
+    with pytest.raises(NotImplementedError):
+        train_one_epoch(torch.nn.Linear(1, 1), None, None, [], None, None, "cpu", 0, None, normlize_target=True, patch_size=4,
+                        args=types.SimpleNamespace(num_view=2))
+
+
+def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception as e:  # report instead of letting the parent wait for its timeout
+        q.put((rank, repr(e)))
+
+
+def _worker_body(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dig_b200 import dist_layout
+    from oracle import restatement as R
+    torch.manual_seed(0)
+    Q, C, T = 6, 16, 0.2
+    q_all = torch.randn(world, 2 * Q, C)          # [q1 ; q2] per rank
+    k_all = torch.nn.functional.normalize(torch.randn(world, 2 * Q, C), dim=-1)
+    k1, k2 = dist_layout.gather_keys(k_all[rank].clone())
+    # rank-ordered concatenation, exactly torch.cat(all_gather(...)) of the reference
+    ok = torch.equal(k1, k_all[:, :Q].reshape(world * Q, C)) and torch.equal(k2, k_all[:, Q:].reshape(world * Q, C))
+    l1, a1, _ = R.contrastive_loss(q_all[rank, :Q], k2, T, rank)
+    # single-process equivalent: all queries against all keys with global labels; per-rank loss is the mean over its own rows
+    logits = torch.nn.functional.normalize(q_all[:, :Q].reshape(world * Q, C), dim=1) @ k2.t() / T
+    labels = torch.arange(world * Q)
+    ce = torch.nn.functional.cross_entropy(logits, labels, reduction="none") * (2 * T)
+    ok = ok and abs(float(l1) - float(ce[rank * Q:(rank + 1) * Q].mean())) < 1e-5
+    ok = ok and dist_layout.label_offset(Q, rank) == rank * Q
+    stats = torch.tensor([1.0 + rank, 2.0])
+    cnt = dist_layout.sync_batch_stats(stats, 10)
+    ok = ok and cnt == 10.0 * world and float(stats[0]) == sum(1.0 + r for r in range(world)) and float(stats[1]) == 2.0 * world
+    m = utils.SmoothedValue()
+    m.update(float(rank + 1), n=1)
+    m.synchronize_between_processes()
+    ok = ok and m.global_avg == pytest.approx(sum(r + 1 for r in range(world)) / world)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_layout_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
