@@ -256,12 +256,13 @@ def gpu_arm(a):
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), timed per launch with CUDA events in a separate pass ----
     roof = None
+    ops.profile_gemm(True)      # every rank runs the two extra steps (they contain collectives); rank 0 reports
+    for _ in range(2):
+        step_resident()
+    torch.cuda.synchronize()
+    flops, gms, n = ops.profile_gemm(False)
+    sync_all()
     if rank == 0:
-        ops.profile_gemm(True)
-        for _ in range(2):
-            step_resident()
-        torch.cuda.synchronize()
-        flops, gms, n = ops.profile_gemm(False)
         peak, hbm, how = peaks()
         ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all encoder/head GEMM launches of the step)", "achieved": ach,
