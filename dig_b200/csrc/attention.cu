@@ -131,11 +131,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       if (P_TMEM) {
         tmem_st16(tl + (c >> 1), pk);
       } else {
-        uint8_t* base = sP + (c >> 6) * 16384;
+        const uint32_t base = smem_u32(sP) + (c >> 6) * 16384;
         const uint32_t ch0 = (c & 63) >> 3;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
-          *reinterpret_cast<uint4*>(base + sw128_offset(t, ch0 + jj)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          sts_u4(base + sw128_offset(t, ch0 + jj), make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]));
       }
     }
     if (P_TMEM) tmem_st_wait();
@@ -293,6 +293,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
     int mma_seen = 0;
     int it = 0;
+    const uint32_t sP_s = smem_u32(sP), sdS_s = smem_u32(sdS);
     for (int j = 0; j < 2; ++j) {
       for (int i = 0; i < 2; ++i, ++it) {
         mbar_wait(bar_sdp, it & 1);
@@ -319,8 +320,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const uint32_t off = sub + sw128_offset(t, ch0 + jj);
-            *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[4 * jj], pp[4 * jj + 1], pp[4 * jj + 2], pp[4 * jj + 3]);
-            *reinterpret_cast<uint4*>(sdS + off) = make_uint4(ds[4 * jj], ds[4 * jj + 1], ds[4 * jj + 2], ds[4 * jj + 3]);
+            sts_u4(sP_s + off, make_uint4(pp[4 * jj], pp[4 * jj + 1], pp[4 * jj + 2], pp[4 * jj + 3]));
+            sts_u4(sdS_s + off, make_uint4(ds[4 * jj], ds[4 * jj + 1], ds[4 * jj + 2], ds[4 * jj + 3]));
           }
         }
         fence_proxy_async_smem();

@@ -10,33 +10,15 @@
 // include/dig_b200.h), which covers forward (x.W^T), dgrad (dy.W) and wgrad (dy^T.x) without any transposed
 // copies.  Replaces the cuBLAS calls behind F.linear in the reference (modeling_finetune.py:93,119,54,58;
 // modeling_pretrain_moco_mim_ori.py:463-482,422-426) and their autograd counterparts.
-#include "common.cuh"
-#include "../../include/dig_b200.h"
+#include <stdlib.h>
+
+#include "gemm_epilogue.cuh"
 
 namespace dig {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kEpiWarps = 8;
 static constexpr int kGemmThreads = 64 + kEpiWarps * 32;
-
-struct GemmEpilogue {
-  void* out;
-  long long ldo;
-  int out_fp32;
-  const float* bias;
-  const float* residual;
-  long long ldr;
-  long long res_row_mod;
-  const uint8_t* row_mask;
-  const float* row_mask_value;
-  int mode;
-  void* aux;
-  long long ldaux;
-  float alpha;
-  int atomic;
-  float* colsum;
-};
 
 template <int BN>
 struct GemmSmem {
@@ -49,16 +31,7 @@ struct GemmSmem {
   static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
-  const uint2 v = *reinterpret_cast<const uint2*>(p);
-  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
-}
-__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float4 v) {
-  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-}
-
 // MODE: DIG_EPI_* or kEpiAtomic (split-K fp32 accumulate); OUT_F32: output element type.
-static constexpr int kEpiAtomic = 4;
 
 template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -181,16 +154,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int quarter = warp & 3;
     const int half = ew >> 2;
     float* tile = epi_smem + ew * 1024;
-    const int col4 = lane & 7, rsub = lane >> 3;
-    float* const out_f = reinterpret_cast<float*>(ep.out);
-    __nv_bfloat16* const out_h = reinterpret_cast<__nv_bfloat16*>(ep.out);
-    __nv_bfloat16* const aux = reinterpret_cast<__nv_bfloat16*>(ep.aux);
-    const long long ldo = ep.ldo, ldaux = ep.ldaux, ldr = ep.ldr, res_row_mod = ep.res_row_mod;
-    const float* const bias = ep.bias;
-    const float* const residual = ep.residual;
-    const uint8_t* const row_mask = ep.row_mask;
-    float* const colsum = ep.colsum;
-    const float alpha = ep.alpha;
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int n_blk = w % num_n;
@@ -198,106 +161,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row_base = (long long)m_blk * BM + quarter * 32;
-      const int rows_left = (int)min((long long)32, (long long)M - row_base);
-      // Operands the epilogue reads from HBM (residual rows, or the bf16 aux rows) are requested for every chunk of this warp
-      // BEFORE waiting for the accumulator, so their latency hides behind the tile's MMAs.  Raw bits only: no use before the wait.
-      constexpr int NCH = BN / 64;
-      float4 pre[NCH][8];
-      uint32_t maskbits[NCH];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int gcol_p = n_blk * BN + half * (BN / 2) + ch * 32 + col4 * 4;
-        maskbits[ch] = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + rsub;
-          pre[ch][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gcol_p < N && r < rows_left) {
-            const long long grow = row_base + r;
-            if (MODE == DIG_EPI_LINEAR) {
-              if (residual != nullptr)
-                pre[ch][i] = *reinterpret_cast<const float4*>(residual + (res_row_mod > 0 ? (grow % res_row_mod) : grow) * ldr + gcol_p);
-              if (row_mask != nullptr && row_mask[grow] != 0) maskbits[ch] |= 1u << i;
-            } else if (MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_RELU_MASK) {
-              const uint2 t = *reinterpret_cast<const uint2*>(aux + grow * ldaux + gcol_p);
-              pre[ch][i].x = __uint_as_float(t.x);
-              pre[ch][i].y = __uint_as_float(t.y);
-            }
-          }
-        }
-      }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int cc = ch * 32;
-        const int c = half * (BN / 2) + cc;
-        const int gcol = n_blk * BN + c + col4 * 4;
-        const bool col_ok = gcol < N;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c, v);
-        tmem_ld_wait();
-        if (cc + 32 >= BN / 2) {  // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        __syncwarp();
-        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (MODE != kEpiAtomic && bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rsub;
-            if (r >= rows_left) continue;
-            const long long grow = row_base + r;
-            float4 f = *reinterpret_cast<const float4*>(tile + r * 32 + ((col4 ^ (r & 7)) << 2));
-            f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha;
-            if (MODE == kEpiAtomic) {
-              float* o = out_f + grow * ldo + gcol;
-              atomicAdd(o, f.x); atomicAdd(o + 1, f.y); atomicAdd(o + 2, f.z); atomicAdd(o + 3, f.w);
-              continue;
-            }
-            f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-            if (MODE == DIG_EPI_GELU) {
-              st_bf16x4(aux + grow * ldaux + gcol, f);
-              f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w);
-            } else if (MODE == DIG_EPI_GELU_BWD) {
-              const uint32_t lo = __float_as_uint(pre[ch][i].x), hi = __float_as_uint(pre[ch][i].y);
-              const float4 x = make_float4(bf16_lo(lo), bf16_hi(lo), bf16_lo(hi), bf16_hi(hi));
-              f.x *= gelu_erf_grad(x.x); f.y *= gelu_erf_grad(x.y); f.z *= gelu_erf_grad(x.z); f.w *= gelu_erf_grad(x.w);
-            } else if (MODE == DIG_EPI_RELU_MASK) {
-              const uint32_t lo = __float_as_uint(pre[ch][i].x), hi = __float_as_uint(pre[ch][i].y);
-              const float4 x = make_float4(bf16_lo(lo), bf16_hi(lo), bf16_lo(hi), bf16_hi(hi));
-              f.x = x.x > 0.f ? f.x : 0.f; f.y = x.y > 0.f ? f.y : 0.f; f.z = x.z > 0.f ? f.z : 0.f; f.w = x.w > 0.f ? f.w : 0.f;
-            }
-            if (MODE == DIG_EPI_LINEAR) {
-              if (maskbits[ch] & (1u << i)) f = __ldg(reinterpret_cast<const float4*>(ep.row_mask_value + gcol));
-              f.x += pre[ch][i].x; f.y += pre[ch][i].y; f.z += pre[ch][i].z; f.w += pre[ch][i].w;
-            }
-            if (MODE == DIG_EPI_GELU_BWD) { cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w; }
-            if (OUT_F32) *reinterpret_cast<float4*>(out_f + grow * ldo + gcol) = f;
-            else st_bf16x4(out_h + grow * ldo + gcol, f);
-          }
-        }
-        if (MODE == DIG_EPI_GELU_BWD && colsum != nullptr) {  // column sums of the written tile: bias gradient of fc1
-#pragma unroll
-          for (int o = 8; o <= 16; o <<= 1) {
-            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
-          }
-          if (col_ok && rsub == 0) {
-            atomicAdd(cta_colsum + gcol, cs.x); atomicAdd(cta_colsum + gcol + 1, cs.y);
-            atomicAdd(cta_colsum + gcol + 2, cs.z); atomicAdd(cta_colsum + gcol + 3, cs.w);
-          }
-        }
-        __syncwarp();
-      }
+      const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+      epilogue_warp_tile<BN / 2, MODE, OUT_F32>(ep, tw, n_blk * BN + half * (BN / 2), row_base, M, N, tile, cta_colsum, lane, &tmem_full[acc],
+                                                acc_phase, [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); });
     }
   }
 
@@ -330,12 +196,12 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   split = (num_kb + per - 1) / per;
 
   GemmEpilogue ep;
-  ep.out = g->out; ep.ldo = g->ldo; ep.out_fp32 = g->out_fp32;
+  ep.out = g->out; ep.ldo = g->ldo;
   ep.bias = g->bias; ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
-  ep.mode = g->epilogue; ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
-  ep.atomic = g->split_k > 1 ? 1 : 0;
+  ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.colsum = g->colsum;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
   if (g->colsum) DIG_REQUIRE(g->epilogue == DIG_EPI_GELU_BWD && g->N <= 2048, "dig_gemm: colsum is built for DIG_EPI_GELU_BWD with N <= 2048 only");
 
   auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32>;
@@ -380,6 +246,17 @@ static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
   return -1;
 }
 
+int gemm2_try(const dig_gemm_t* g, cudaStream_t s);  // gemm2.cu: 2-CTA kernel; returns 1 when it does not take the problem
+
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DIG_GEMM_1CTA");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace dig
 
 extern "C" int dig_gemm(const dig_gemm_t* g, void* stream) {
@@ -399,6 +276,10 @@ extern "C" int dig_gemm(const dig_gemm_t* g, void* stream) {
                 "dig_gemm: split_k>1 needs a plain fp32 accumulate epilogue");
   if (g->epilogue != DIG_EPI_LINEAR) DIG_REQUIRE(g->aux != nullptr && g->ldaux % 4 == 0, "dig_gemm: epilogue %d needs aux", g->epilogue);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (use_2cta()) {
+    const int r = gemm2_try(g, s);
+    if (r <= 0) return r;
+  }
   // tile width: 128 wherever N fills it, 64 for the narrow heads (pix_decoder 192/48)
   if (g->N % 128 == 0 || g->N > 256) return dispatch<128>(g, s);
   return dispatch<64>(g, s);

@@ -1,0 +1,320 @@
+// dig_b200 -- 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM.
+//
+// A CTA pair (cluster of 2 on one TPC) owns a 256 x BN output tile.  Each CTA stages only ITS half of the operands -- its own 128
+// rows of A and BN/2 of B's columns -- and the leader CTA issues one tcgen05.mma.cta_group::2 (M = 256) that reads both halves,
+// so every byte fetched over TMA / read from shared memory feeds twice the FLOPs of the 1-CTA 128 x 128 kernel, which is operand-
+// bandwidth bound.  Each CTA drains its own 128 accumulator rows from its own TMEM with the shared epilogue.
+//
+// Barrier protocol (barriers live at identical shared-memory offsets in both CTAs):
+//   full[s]        leader's copy only; 2 arrivals (leader: arrive.expect_tx for BOTH CTAs' bytes, peer: remote arrive); both CTAs'
+//                  TMA loads complete_tx on it (cta_group::2 loads, peer bit cleared in the barrier address)
+//   empty[s]       one per CTA; the leader's tcgen05.commit multicasts the arrival to both
+//   tmem_full[a]   one per CTA; multicast commit after the tile's last MMA
+//   tmem_empty[a]  leader's copy only; 2 x 8 epilogue warps arrive (peer: remote arrive)
+#include <stdlib.h>
+
+#include "gemm_epilogue.cuh"
+
+namespace dig {
+
+static constexpr int BK = 64;
+static constexpr int kGemm2Threads = 64 + kEpiWarps * 32;
+
+template <int BN>
+struct Gemm2Smem {
+  static constexpr int kStageA = 128 * BK * 2;
+  static constexpr int kStageB = (BN / 2) * BK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN == 128) ? 6 : 5;
+  static constexpr int kEpi = kEpiWarps * 32 * 32 * 4;
+  static constexpr int kColsum = 2048 * 4;
+  static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// TMA load issued by either CTA of the pair; transaction bytes are credited to the LEADER's barrier.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {  // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmEpilogue ep, int M, int N,
+                   int K, int split_k, int kb_per_split) {
+  using S = Gemm2Smem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+  constexpr int HB = BN / 2;  // B columns staged by each CTA
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi_smem = reinterpret_cast<float*>(smem + kStages * S::kStage);
+  float* cta_colsum = reinterpret_cast<float*>(smem + kStages * S::kStage + S::kEpi);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStage + S::kEpi + S::kColsum);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int num_m = (M + 255) / 256;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_kb = (K + BK - 1) / BK;
+  const int num_work = num_m * num_n * split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_holder, kTmemCols);
+  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)
+    for (int i = threadIdx.x; i < N; i += kGemm2Threads) cta_colsum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before anyone arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, own halves) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const int n_blk = w % num_n;
+        const int m_blk = (w / num_n) % num_m;
+        const int split = w / (num_n * num_m);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb);
+        const int m0 = m_blk * 256 + (int)rank * 128;
+        const int n0 = n_blk * BN + (int)rank * HB;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStage;
+          uint8_t* sb = sa + S::kStageA;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::kStage);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          if (!A_MN) {
+            tma_load_2d_2sm(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < HB / 64; ++j) tma_load_2d_2sm(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
+        const int split = w / (num_n * num_m);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, num_kb);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStage);
+          const uint32_t sb = sa + S::kStageA;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_sdesc_sw128(sa + k * 2048, 8192, 1024) : make_sdesc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_sdesc_sw128(sb + k * 2048, 8192, 1024) : make_sdesc_sw128(sb + k * 32, 16, 1024);
+            tc_mma_ss_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_2sm(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    float* tile = epi_smem + ew * 1024;
+    int it = 0;
+    for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
+      const int n_blk = w % num_n;
+      const int m_blk = (w / num_n) % num_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const long long row_base = (long long)m_blk * 256 + rank * 128 + quarter * 32;
+      const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * HB;
+      epilogue_warp_tile<HB, MODE, OUT_F32>(ep, tw, n_blk * BN + half * HB, row_base, M, N, tile, cta_colsum, lane, &tmem_full[acc], acc_phase,
+                                            [&]() {
+                                              if (lane == 0) {
+                                                if (leader) mbar_arrive(&tmem_empty[acc]);
+                                                else mbar_arrive_remote(&tmem_empty[acc], 0);
+                                              }
+                                            });
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the pair leaves together: the leader's MMAs read the peer's shared memory, arrivals are remote
+  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)
+    for (int i = threadIdx.x; i < N; i += kGemm2Threads) atomicAdd(ep.colsum + i, cta_colsum[i]);
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
+static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
+  using S = Gemm2Smem<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!g->a_mn_major) rc = make_tmap_bf16_2d(&ta, g->A, (uint64_t)g->M, (uint64_t)g->K, (uint64_t)g->lda, 128, BK);
+  else rc = make_tmap_bf16_2d(&ta, g->A, (uint64_t)g->K, (uint64_t)g->M, (uint64_t)g->lda, BK, 64);
+  if (rc) return rc;
+  if (!g->b_mn_major) rc = make_tmap_bf16_2d(&tb, g->B, (uint64_t)g->N, (uint64_t)g->K, (uint64_t)g->ldb, BN / 2, BK);
+  else rc = make_tmap_bf16_2d(&tb, g->B, (uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->ldb, BK, 64);
+  if (rc) return rc;
+
+  const int num_m = (int)((g->M + 255) / 256), num_n = (int)((g->N + BN - 1) / BN), num_kb = (int)((g->K + BK - 1) / BK);
+  int split = g->split_k > 1 ? g->split_k : 1;
+  if (split > num_kb) split = num_kb;
+  const int per = (num_kb + split - 1) / split;
+  split = (num_kb + per - 1) / per;
+
+  GemmEpilogue ep;
+  ep.out = g->out; ep.ldo = g->ldo;
+  ep.bias = g->bias; ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
+  ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
+  ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
+  ep.colsum = g->colsum;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
+
+  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
+    attr_set = true;
+  }
+  const long long work = (long long)num_m * num_n * split;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = (int)(work < max_clusters ? work : max_clusters);
+  kern<<<clusters * 2, kGemm2Threads, S::kBytes, stream>>>(ta, tb, ep, (int)g->M, (int)g->N, (int)g->K, split, per);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Returns 1 when the combination is not built for the 2-CTA kernel (caller falls back to the 1-CTA kernel), 0 on success, <0 on error.
+template <int BN>
+static int dispatch2(const dig_gemm_t* g, cudaStream_t s) {
+  const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0, f32 = g->out_fp32 != 0;
+  const int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+#define DIG_CASE(A, B, MODE, F32) \
+  if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm2<BN, A, B, MODE, F32>(g, s);
+  DIG_CASE(false, false, DIG_EPI_LINEAR, false)
+  DIG_CASE(false, false, DIG_EPI_LINEAR, true)
+  DIG_CASE(false, false, DIG_EPI_GELU, false)
+  if constexpr (BN != 192) {  // MN-major B is staged in 64-column boxes: BN/2 must be a multiple of 64
+    DIG_CASE(false, true, DIG_EPI_LINEAR, false)
+    DIG_CASE(false, true, DIG_EPI_LINEAR, true)
+    DIG_CASE(false, true, DIG_EPI_GELU_BWD, false)
+    DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)
+    DIG_CASE(true, true, DIG_EPI_LINEAR, true)
+    DIG_CASE(true, true, kEpiAtomic, true)
+  }
+#undef DIG_CASE
+  return 1;
+}
+
+int gemm2_try(const dig_gemm_t* g, cudaStream_t s) {
+  // 2-CTA tiles are 256 rows tall: keep small problems (few tiles) on the 1-CTA kernel so they still spread over the SMs
+  const long long m_tiles = (g->M + 255) / 256;
+  const bool bmn = g->b_mn_major != 0;
+  int bn;
+  if (g->N % 256 == 0) bn = 256;
+  else if (g->N % 192 == 0 && !bmn) bn = 192;
+  else if (g->N % 128 == 0) bn = 128;
+  else return 1;
+  const long long split = g->split_k > 1 ? g->split_k : 1;
+  if (m_tiles * ((g->N + bn - 1) / bn) * split < 32) return 1;
+  // Measured on B200 (scripts/gemm_dbg2.py): with K < 768 the tile time is set by the epilogue, where the 1-CTA kernel's smaller
+  // tiles overlap better; the 2-CTA mainloop only pays off once the K loop dominates.  Override with DIG_GEMM_2CTA_MINK.
+  static int min_k = -1;
+  if (min_k < 0) { const char* e = getenv("DIG_GEMM_2CTA_MINK"); min_k = e ? atoi(e) : 768; }
+  if (g->K < min_k || split > 1) return 1;
+  if (bn == 256) return dispatch2<256>(g, s);
+  if (bn == 192) return dispatch2<192>(g, s);
+  return dispatch2<128>(g, s);
+}
+
+}  // namespace dig
