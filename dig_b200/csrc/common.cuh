@@ -32,6 +32,8 @@ void set_last_error(const char* fmt, ...);
 // 128-byte swizzle.  Returns 0 on success.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols);
+int make_tmap_2d(CUtensorMap* out, const void* base, int is_fp32, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                 uint32_t box_rows, uint32_t box_cols);
 int num_sms();
 
 #ifdef __CUDACC__

@@ -12,7 +12,7 @@
 // modeling_pretrain_moco_mim_ori.py:463-482,422-426) and their autograd counterparts.
 #include <stdlib.h>
 
-#include "gemm_epilogue.cuh"
+#include "gemm_epilogue_tma.cuh"
 
 namespace dig {
 
@@ -20,24 +20,26 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int kGemmThreads = 64 + kEpiWarps * 32;
 
-template <int BN>
+template <int BN, bool TMA_EPI>
 struct GemmSmem {
   static constexpr int kStageA = BM * BK * 2;
   static constexpr int kStageB = BN * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 128) ? 5 : 6;
-  static constexpr int kEpi = kEpiWarps * 32 * 32 * 4;  // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int kStages = (BN == 128) ? (TMA_EPI ? 4 : 5) : 6;
+  // epilogue scratch: one 32x32 fp32 transpose tile per warp (generic epilogue) or two 32 x 128 B TMA staging tiles per warp
+  static constexpr int kEpi = TMA_EPI ? kEpiTmaBytes : kEpiWarps * 32 * 32 * 4;
   static constexpr int kColsum = 2048 * 4;               // per-CTA column-sum scratch (N <= 2048 when colsum is requested)
-  static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // MODE: DIG_EPI_* or kEpiAtomic (split-K fp32 accumulate); OUT_F32: output element type.
 
-template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool TMA_EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmEpilogue ep, int M,
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux, GemmEpilogue ep, int M,
                   int N, int K, int split_k, int kb_per_split) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, TMA_EPI>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   constexpr uint32_t kIdesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
@@ -52,6 +54,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]        epilogue -> MMA
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_ld_bar = bars + 2 * kStages + 5;  // [kEpiWarps][2] TMA loads into the epilogue staging tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -64,6 +67,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (TMA_EPI) { tma_prefetch_desc(&tma_out); tma_prefetch_desc(&tma_aux); }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -72,6 +76,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kEpiWarps);
     }
+    if (TMA_EPI)
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_ld_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, kTmemCols);
@@ -154,6 +160,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int quarter = warp & 3;
     const int half = ew >> 2;
     float* tile = epi_smem + ew * 1024;
+    EpiTmaState st;
+    st.stage_s = smem_u32(epi_smem) + (uint32_t)ew * 2u * kStageTileBytes;
+    st.ld_bar = epi_ld_bar + 2 * ew;
+    st.uses0 = st.uses1 = 0;
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int n_blk = w % num_n;
@@ -161,10 +171,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row_base = (long long)m_blk * BM + quarter * 32;
-      const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
-      epilogue_warp_tile<BN / 2, MODE, OUT_F32>(ep, tw, n_blk * BN + half * (BN / 2), row_base, M, N, tile, cta_colsum, lane, &tmem_full[acc],
-                                                acc_phase, [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); });
+      auto release = [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); };
+      if constexpr (TMA_EPI) {
+        const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+        epilogue_warp_tile_tma<BN, MODE, OUT_F32>(ep, &tma_out, &tma_aux, st, tw, n_blk * BN, (int)row_base, N, half, cta_colsum, lane,
+                                                  &tmem_full[acc], acc_phase, release);
+      } else {
+        const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+        epilogue_warp_tile<BN / 2, MODE, OUT_F32>(ep, tw, n_blk * BN + half * (BN / 2), row_base, M, N, tile, cta_colsum, lane,
+                                                  &tmem_full[acc], acc_phase, release);
+      }
     }
+    if (TMA_EPI && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -177,9 +195,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool TMA_EPI>
 static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, TMA_EPI>;
   CUtensorMap ta, tb;
   int rc;
   if (!g->a_mn_major) rc = make_tmap_bf16_2d(&ta, g->A, (uint64_t)g->M, (uint64_t)g->K, (uint64_t)g->lda, BM, BK);
@@ -188,6 +206,14 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   if (!g->b_mn_major) rc = make_tmap_bf16_2d(&tb, g->B, (uint64_t)g->N, (uint64_t)g->K, (uint64_t)g->ldb, BN, BK);
   else rc = make_tmap_bf16_2d(&tb, g->B, (uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->ldb, BK, 64);
   if (rc) return rc;
+  CUtensorMap to = ta, tx = ta;  // unused by the generic epilogue
+  if (TMA_EPI) {
+    rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
+    if (rc) return rc;
+    if (MODE == DIG_EPI_GELU || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
+    if (rc) return rc;
+  }
 
   const int num_m = (int)((g->M + BM - 1) / BM), num_n = (int)((g->N + BN - 1) / BN), num_kb = (int)((g->K + BK - 1) / BK);
   int split = g->split_k > 1 ? g->split_k : 1;
@@ -204,7 +230,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
   if (g->colsum) DIG_REQUIRE(g->epilogue == DIG_EPI_GELU_BWD && g->N <= 2048, "dig_gemm: colsum is built for DIG_EPI_GELU_BWD with N <= 2048 only");
 
-  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32>;
+  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32, TMA_EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     DIG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
@@ -212,7 +238,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   }
   const long long work = (long long)num_m * num_n * split;
   const int grid = (int)(work < num_sms() ? work : num_sms());
-  kern<<<grid, kGemmThreads, S::kBytes, stream>>>(ta, tb, ep, (int)g->M, (int)g->N, (int)g->K, split, per);
+  kern<<<grid, kGemmThreads, S::kBytes, stream>>>(ta, tb, to, tx, ep, (int)g->M, (int)g->N, (int)g->K, split, per);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -223,17 +249,23 @@ template <int BN>
 static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0, f32 = g->out_fp32 != 0;
   const int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+  const bool tma_ok = tma_epilogue_ok(g);
 #define DIG_CASE(A, B, MODE, F32) \
-  if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm<BN, A, B, MODE, F32>(g, s);
-  DIG_CASE(false, false, DIG_EPI_LINEAR, false)   // forward Linear -> bf16 (qkv, pix_decoder)
-  DIG_CASE(false, false, DIG_EPI_LINEAR, true)    // forward Linear -> fp32 (+bias +residual, patch embed, BN-MLP heads)
-  DIG_CASE(false, false, DIG_EPI_GELU, false)     // fc1 + GELU
-  DIG_CASE(false, true, DIG_EPI_LINEAR, false)    // dgrad -> bf16
-  DIG_CASE(false, true, DIG_EPI_LINEAR, true)     // dgrad -> fp32
-  DIG_CASE(false, true, DIG_EPI_GELU_BWD, false)  // fc2 dgrad * gelu'
+  if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm<BN, A, B, MODE, F32, false>(g, s);
+#define DIG_CASE_T(A, B, MODE, F32)                                              \
+  if (amn == A && bmn == B && mode == MODE && f32 == F32) {                      \
+    if (tma_ok) return launch_gemm<BN, A, B, MODE, F32, true>(g, s);                      \
+    return launch_gemm<BN, A, B, MODE, F32, false>(g, s);                                 \
+  }
+  DIG_CASE_T(false, false, DIG_EPI_LINEAR, false)   // forward Linear -> bf16 (qkv, pix_decoder)
+  DIG_CASE_T(false, false, DIG_EPI_LINEAR, true)    // forward Linear -> fp32 (+bias +residual, patch embed, BN-MLP heads)
+  DIG_CASE_T(false, false, DIG_EPI_GELU, false)     // fc1 + GELU
+  DIG_CASE_T(false, true, DIG_EPI_LINEAR, false)    // dgrad -> bf16
+  DIG_CASE_T(false, true, DIG_EPI_LINEAR, true)     // dgrad -> fp32
+  DIG_CASE_T(false, true, DIG_EPI_GELU_BWD, false)  // fc2 dgrad * gelu'
   DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)  // BN-MLP dgrad through ReLU
-  DIG_CASE(true, true, DIG_EPI_LINEAR, true)      // wgrad, single pass
-  DIG_CASE(true, true, kEpiAtomic, true)          // wgrad, split-K
+  DIG_CASE_T(true, true, DIG_EPI_LINEAR, true)      // wgrad, single pass
+  DIG_CASE_T(true, true, kEpiAtomic, true)          // wgrad, split-K
   DIG_CASE(true, true, DIG_EPI_LINEAR, false)
   DIG_CASE(true, false, DIG_EPI_LINEAR, true)
   DIG_CASE(true, false, DIG_EPI_LINEAR, false)
@@ -241,6 +273,7 @@ static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
   DIG_CASE(false, true, kEpiAtomic, true)
   DIG_CASE(true, false, kEpiAtomic, true)
 #undef DIG_CASE
+#undef DIG_CASE_T
   set_last_error("dig_gemm: combination not built (a_mn=%d b_mn=%d epilogue=%d split_k=%d out_fp32=%d)", (int)amn, (int)bmn, g->epilogue,
                  g->split_k, (int)f32);
   return -1;

@@ -13,22 +13,22 @@
 //   tmem_empty[a]  leader's copy only; 2 x 8 epilogue warps arrive (peer: remote arrive)
 #include <stdlib.h>
 
-#include "gemm_epilogue.cuh"
+#include "gemm_epilogue_tma.cuh"
 
 namespace dig {
 
 static constexpr int BK = 64;
 static constexpr int kGemm2Threads = 64 + kEpiWarps * 32;
 
-template <int BN>
+template <int BN, bool TMA_EPI>
 struct Gemm2Smem {
   static constexpr int kStageA = 128 * BK * 2;
   static constexpr int kStageB = (BN / 2) * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 128) ? 6 : 5;
-  static constexpr int kEpi = kEpiWarps * 32 * 32 * 4;
+  static constexpr int kStages = (BN == 128) ? 6 : (TMA_EPI ? 4 : 5);
+  static constexpr int kEpi = TMA_EPI ? kEpiTmaBytes : kEpiWarps * 32 * 32 * 4;
   static constexpr int kColsum = 2048 * 4;
-  static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 + 256;
+  static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 + 512;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -77,11 +77,12 @@ __device__ __forceinline__ void tc_mma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, 
       : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool TMA_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
-gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmEpilogue ep, int M, int N,
+gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux, GemmEpilogue ep, int M, int N,
                    int K, int split_k, int kb_per_split) {
-  using S = Gemm2Smem<BN>;
+  using S = Gemm2Smem<BN, TMA_EPI>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t kIdesc = make_idesc_bf16(256, BN, A_MN, B_MN);
@@ -97,6 +98,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_ld_bar = bars + 2 * kStages + 5;  // [kEpiWarps][2] TMA loads into the epilogue staging tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +115,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (TMA_EPI) { tma_prefetch_desc(&tma_out); tma_prefetch_desc(&tma_aux); }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 2);
       mbar_init(&empty_bar[i], 1);
@@ -121,6 +124,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * kEpiWarps);
     }
+    if (TMA_EPI)
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&epi_ld_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_holder, kTmemCols);
@@ -205,6 +210,10 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const int quarter = warp & 3;
     const int half = ew >> 2;
     float* tile = epi_smem + ew * 1024;
+    EpiTmaState st;
+    st.stage_s = smem_u32(epi_smem) + (uint32_t)ew * 2u * kStageTileBytes;
+    st.ld_bar = epi_ld_bar + 2 * ew;
+    st.uses0 = st.uses1 = 0;
     int it = 0;
     for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
       const int n_blk = w % num_n;
@@ -212,15 +221,23 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row_base = (long long)m_blk * 256 + rank * 128 + quarter * 32;
-      const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * HB;
-      epilogue_warp_tile<HB, MODE, OUT_F32>(ep, tw, n_blk * BN + half * HB, row_base, M, N, tile, cta_colsum, lane, &tmem_full[acc], acc_phase,
-                                            [&]() {
-                                              if (lane == 0) {
-                                                if (leader) mbar_arrive(&tmem_empty[acc]);
-                                                else mbar_arrive_remote(&tmem_empty[acc], 0);
-                                              }
-                                            });
+      auto release = [&]() {
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_remote(&tmem_empty[acc], 0);
+        }
+      };
+      if constexpr (TMA_EPI) {
+        const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+        epilogue_warp_tile_tma<BN, MODE, OUT_F32>(ep, &tma_out, &tma_aux, st, tw, n_blk * BN, (int)row_base, N, half, cta_colsum, lane,
+                                                  &tmem_full[acc], acc_phase, release);
+      } else {
+        const uint32_t tw = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * HB;
+        epilogue_warp_tile<HB, MODE, OUT_F32>(ep, tw, n_blk * BN + half * HB, row_base, M, N, tile, cta_colsum, lane, &tmem_full[acc],
+                                              acc_phase, release);
+      }
     }
+    if (TMA_EPI && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -234,9 +251,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool TMA_EPI>
 static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
-  using S = Gemm2Smem<BN>;
+  using S = Gemm2Smem<BN, TMA_EPI>;
   CUtensorMap ta, tb;
   int rc;
   if (!g->a_mn_major) rc = make_tmap_bf16_2d(&ta, g->A, (uint64_t)g->M, (uint64_t)g->K, (uint64_t)g->lda, 128, BK);
@@ -245,6 +262,14 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   if (!g->b_mn_major) rc = make_tmap_bf16_2d(&tb, g->B, (uint64_t)g->N, (uint64_t)g->K, (uint64_t)g->ldb, BN / 2, BK);
   else rc = make_tmap_bf16_2d(&tb, g->B, (uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->ldb, BK, 64);
   if (rc) return rc;
+  CUtensorMap to = ta, tx = ta;  // unused by the generic epilogue
+  if (TMA_EPI) {
+    rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
+    if (rc) return rc;
+    if (MODE == DIG_EPI_GELU || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
+    if (rc) return rc;
+  }
 
   const int num_m = (int)((g->M + 255) / 256), num_n = (int)((g->N + BN - 1) / BN), num_kb = (int)((g->K + BK - 1) / BK);
   int split = g->split_k > 1 ? g->split_k : 1;
@@ -260,7 +285,7 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   ep.colsum = g->colsum;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
 
-  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32>;
+  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32, TMA_EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     DIG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
@@ -269,7 +294,7 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   const long long work = (long long)num_m * num_n * split;
   const int max_clusters = num_sms() / 2;
   const int clusters = (int)(work < max_clusters ? work : max_clusters);
-  kern<<<clusters * 2, kGemm2Threads, S::kBytes, stream>>>(ta, tb, ep, (int)g->M, (int)g->N, (int)g->K, split, per);
+  kern<<<clusters * 2, kGemm2Threads, S::kBytes, stream>>>(ta, tb, to, tx, ep, (int)g->M, (int)g->N, (int)g->K, split, per);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -279,20 +304,27 @@ template <int BN>
 static int dispatch2(const dig_gemm_t* g, cudaStream_t s) {
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0, f32 = g->out_fp32 != 0;
   const int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+  const bool tma_ok = tma_epilogue_ok(g);
 #define DIG_CASE(A, B, MODE, F32) \
-  if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm2<BN, A, B, MODE, F32>(g, s);
-  DIG_CASE(false, false, DIG_EPI_LINEAR, false)
-  DIG_CASE(false, false, DIG_EPI_LINEAR, true)
-  DIG_CASE(false, false, DIG_EPI_GELU, false)
+  if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm2<BN, A, B, MODE, F32, false>(g, s);
+#define DIG_CASE_T(A, B, MODE, F32)                                              \
+  if (amn == A && bmn == B && mode == MODE && f32 == F32) {                      \
+    if (tma_ok) return launch_gemm2<BN, A, B, MODE, F32, true>(g, s);                      \
+    return launch_gemm2<BN, A, B, MODE, F32, false>(g, s);                                 \
+  }
+  DIG_CASE_T(false, false, DIG_EPI_LINEAR, false)
+  DIG_CASE_T(false, false, DIG_EPI_LINEAR, true)
+  DIG_CASE_T(false, false, DIG_EPI_GELU, false)
   if constexpr (BN != 192) {  // MN-major B is staged in 64-column boxes: BN/2 must be a multiple of 64
-    DIG_CASE(false, true, DIG_EPI_LINEAR, false)
-    DIG_CASE(false, true, DIG_EPI_LINEAR, true)
-    DIG_CASE(false, true, DIG_EPI_GELU_BWD, false)
+    DIG_CASE_T(false, true, DIG_EPI_LINEAR, false)
+    DIG_CASE_T(false, true, DIG_EPI_LINEAR, true)
+    DIG_CASE_T(false, true, DIG_EPI_GELU_BWD, false)
     DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)
-    DIG_CASE(true, true, DIG_EPI_LINEAR, true)
-    DIG_CASE(true, true, kEpiAtomic, true)
+    DIG_CASE_T(true, true, DIG_EPI_LINEAR, true)
+    DIG_CASE_T(true, true, kEpiAtomic, true)
   }
 #undef DIG_CASE
+#undef DIG_CASE_T
   return 1;
 }
 
@@ -307,11 +339,12 @@ int gemm2_try(const dig_gemm_t* g, cudaStream_t s) {
   else return 1;
   const long long split = g->split_k > 1 ? g->split_k : 1;
   if (m_tiles * ((g->N + bn - 1) / bn) * split < 32) return 1;
-  // Measured on B200 (scripts/gemm_dbg2.py): with K < 768 the tile time is set by the epilogue, where the 1-CTA kernel's smaller
-  // tiles overlap better; the 2-CTA mainloop only pays off once the K loop dominates.  Override with DIG_GEMM_2CTA_MINK.
+  // Measured on B200 (scripts/gemm_dbg.py, gemm_dbg2.py): with the TMA-staged epilogue the 2-CTA kernel wins or ties everywhere except
+  // the erf-GELU forward epilogue, which is issue-bound and overlaps better with the 1-CTA kernel's smaller tiles, and split-K, where
+  // the 1-CTA kernel spreads the K slices over more CTAs.  DIG_GEMM_2CTA_MINK raises the K threshold for experiments.
   static int min_k = -1;
-  if (min_k < 0) { const char* e = getenv("DIG_GEMM_2CTA_MINK"); min_k = e ? atoi(e) : 768; }
-  if (g->K < min_k || split > 1) return 1;
+  if (min_k < 0) { const char* e = getenv("DIG_GEMM_2CTA_MINK"); min_k = e ? atoi(e) : 0; }
+  if (g->K < min_k || split > 1 || g->epilogue == DIG_EPI_GELU) return 1;
   if (bn == 256) return dispatch2<256>(g, s);
   if (bn == 192) return dispatch2<192>(g, s);
   return dispatch2<128>(g, s);

@@ -1,0 +1,227 @@
+// dig_b200 -- TMA-staged GEMM epilogue (the fast path; gemm_epilogue.cuh keeps the generic transposing one).
+//
+// Each epilogue warp keeps its accumulator rows in registers in the natural tcgen05.ld layout (one output row per thread), does the
+// fused math there (bias straight from L1 with warp-uniform addresses), and writes 128-byte row segments into a per-warp, 128B-
+// swizzled 32 x 128 B staging tile that a single elected lane hands to the TMA engine (cp.async.bulk.tensor store, or
+// cp.reduce.async.bulk .add for split-K accumulation).  Operands the epilogue needs from HBM -- the fp32 residual rows, or the bf16
+// GELU pre-activation -- arrive the same way: a TMA load into the staging tile, issued one group ahead (the first one before the
+// accumulator wait), and the result is written back in place.  Epilogue warps therefore issue no global loads/stores at all, HBM
+// traffic is whole 128-byte lines, and tails are clipped by the tensor maps.
+#pragma once
+#include <stdlib.h>
+
+#include "gemm_epilogue.cuh"
+
+namespace dig {
+
+static constexpr int kStageTileBytes = 4096;                       // 32 rows x 128 B
+static constexpr int kEpiTmaBytes = kEpiWarps * 2 * kStageTileBytes;  // two staging tiles per epilogue warp
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem, int c_inner, int c_outer) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+// Per-warp persistent state of the TMA epilogue (lives in registers across tiles).
+struct EpiTmaState {
+  uint32_t stage_s;   // shared address of this warp's two staging tiles
+  uint64_t* ld_bar;   // two mbarriers (one per staging tile) for TMA loads into them
+  uint32_t uses0, uses1;  // completed-load counters -> phase parity of ld_bar[0/1]
+};
+
+// One epilogue warp, one output tile.  BNT = tile width in columns; this warp handles the 128-byte column groups gi = half, half+2, ...
+// of its 32 rows.  tmem_warp = TMEM address of the warp's lane quarter at the tile's first accumulator column.
+template <int BNT, int MODE, bool OUT_F32, typename Release>
+__device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, const CUtensorMap* tm_out, const CUtensorMap* tm_aux,
+                                                       EpiTmaState& st, uint32_t tmem_warp, int n0, int row_base, int N, int half,
+                                                       float* cta_colsum, int lane, uint64_t* tmem_full, uint32_t full_phase,
+                                                       Release release) {
+  constexpr int G = OUT_F32 ? 32 : 64;            // columns per 128-byte staging row
+  constexpr int NGT = (BNT + G - 1) / G;          // column groups in the tile
+  static_assert(BNT % G == 0, "tile width must be a multiple of the staging group");
+  const bool has_ld = (MODE == DIG_EPI_GELU_BWD) || (MODE == DIG_EPI_LINEAR && OUT_F32 && ep.residual != nullptr);
+  const uint32_t row_s = (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+
+  // first group's operand load, before the accumulator wait
+  if (lane == 0) tma_store_wait_read_all();       // staging tiles of the previous output tile are free again
+  __syncwarp();
+  if (has_ld && half < NGT && lane == 0) {
+    mbar_expect_tx(&st.ld_bar[0], kStageTileBytes);
+    tma_load_2d_addr(st.stage_s, tm_aux, &st.ld_bar[0], n0 + half * G, row_base);
+  }
+  mbar_wait(tmem_full, full_phase);
+  tc_fence_after();
+  if (half >= NGT) {  // narrow tile: this warp owns no column group, it only hands the accumulator back
+    __syncwarp();
+    release();
+    return;
+  }
+
+  int k = 0;
+#pragma unroll
+  for (int gi0 = 0; gi0 < NGT; gi0 += 2, ++k) {
+    const int gi = gi0 + half;
+    if (gi >= NGT) break;
+    const bool last = (gi + 2 >= NGT);
+    const int gcol = n0 + gi * G;
+    const uint32_t buf = st.stage_s + (uint32_t)((MODE == DIG_EPI_GELU) ? 0 : (k & 1)) * kStageTileBytes;
+    const uint32_t buf2 = st.stage_s + kStageTileBytes;   // GELU forward: second output (post-activation)
+    if (k > 0) {  // the staging tile we are about to overwrite (or prefetch into) must have been read by its TMA store
+      if (lane == 0) {
+        if (has_ld || MODE == DIG_EPI_GELU) tma_store_wait_read_all();
+        else tma_store_wait_read_1();      // double-buffered: only the store issued two groups ago has to be done
+      }
+      __syncwarp();
+    }
+    if (has_ld) {
+      if (!last && lane == 0) {  // prefetch the next group's operand into the other staging tile
+        uint64_t* nb = &st.ld_bar[(k + 1) & 1];
+        mbar_expect_tx(nb, kStageTileBytes);
+        tma_load_2d_addr(st.stage_s + (uint32_t)((k + 1) & 1) * kStageTileBytes, tm_aux, nb, gcol + 2 * G, row_base);
+      }
+      if (k & 1) { mbar_wait(&st.ld_bar[1], st.uses1 & 1); ++st.uses1; }
+      else { mbar_wait(&st.ld_bar[0], st.uses0 & 1); ++st.uses0; }
+    }
+    // accumulator rows -> registers
+    uint32_t v[G];
+    {
+      uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+      tmem_ld32(tmem_warp + gi * G, v0);
+      if (G == 64) {
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[G - 32]);
+        tmem_ld32(tmem_warp + gi * G + 32, v1);
+      }
+      tmem_ld_wait();
+    }
+    if (last) {
+      tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    const float alpha = ep.alpha;
+    if (OUT_F32) {
+      // 8 units of 4 fp32 columns
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+        if (alpha != 1.0f) { f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha; }
+        const uint32_t a = buf + row_s + (((uint32_t)j ^ sw) << 4);
+        if (MODE == DIG_EPI_LINEAR) {
+          if (ep.bias != nullptr && gcol + 4 * j < N) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 4 * j));
+            f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+          }
+          if (has_ld) {
+            const float4 r4 = lds_f4(a);
+            f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
+          }
+        }
+        sts_f4(a, f);
+      }
+    } else {
+      // 8 units of 8 bf16 columns
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]) * alpha;
+        if (ep.bias != nullptr && gcol + 8 * j < N) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 8 * j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 8 * j + 4));
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        const uint32_t off = row_s + (((uint32_t)j ^ sw) << 4);
+        if (MODE == DIG_EPI_GELU) {
+          sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+          sts_u4(buf2 + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+        } else {
+          if (MODE == DIG_EPI_GELU_BWD) {
+            const uint4 x = lds_u4(buf + off);
+            f[0] *= gelu_erf_grad(bf16_lo(x.x)); f[1] *= gelu_erf_grad(bf16_hi(x.x));
+            f[2] *= gelu_erf_grad(bf16_lo(x.y)); f[3] *= gelu_erf_grad(bf16_hi(x.y));
+            f[4] *= gelu_erf_grad(bf16_lo(x.z)); f[5] *= gelu_erf_grad(bf16_hi(x.z));
+            f[6] *= gelu_erf_grad(bf16_lo(x.w)); f[7] *= gelu_erf_grad(bf16_hi(x.w));
+          }
+          sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+        }
+      }
+    }
+    if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr) {
+      // column sums of the staged 32 x 64 bf16 tile: lane l owns columns 2l, 2l+1 (bias gradient of fc1)
+      __syncwarp();
+      float s0 = 0.f, s1 = 0.f;   // rows past M are exact zeros (zero-filled A rows), so they need no masking
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const uint32_t w = lds_u32(buf + (uint32_t)r * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)lane & 3u) << 2));
+        s0 += bf16_lo(w);
+        s1 += bf16_hi(w);
+      }
+      const int c = gcol + 2 * lane;
+      if (c < N) {
+        const uint32_t cs_s = smem_u32(cta_colsum + c);
+        red_shared_add_f32(cs_s, s0);
+        red_shared_add_f32(cs_s + 4, s1);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (MODE == kEpiAtomic) tma_reduce_add_2d(tm_out, buf, gcol, row_base);
+      else if (MODE == DIG_EPI_GELU) {
+        tma_store_2d(tm_aux, buf, gcol, row_base);   // pre-activation
+        tma_store_2d(tm_out, buf2, gcol, row_base);  // gelu(pre)
+      } else tma_store_2d(tm_out, buf, gcol, row_base);
+      tma_store_commit();
+    }
+  }
+}
+
+// Host: can this problem use the TMA-staged epilogue?  (tensor maps need 16-byte aligned bases / strides; the row-mask and position-
+// table epilogue of the patch embed and the ReLU-mask epilogue stay on the generic path).  DIG_GEMM_TMA_EPI=0 disables it.
+static inline bool tma_epilogue_ok(const dig_gemm_t* g) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("DIG_GEMM_TMA_EPI"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return false;
+  const int es = g->out_fp32 ? 4 : 2;
+  if (g->row_mask || g->res_row_mod > 0) return false;
+  if (g->epilogue == DIG_EPI_RELU_MASK) return false;
+  if ((g->N * es) % 16 || (g->ldo * es) % 16 || ((uintptr_t)g->out & 15)) return false;
+  if (g->epilogue == DIG_EPI_GELU || g->epilogue == DIG_EPI_GELU_BWD) {
+    if (g->out_fp32 || (g->ldaux * 2) % 16 || ((uintptr_t)g->aux & 15)) return false;
+  }
+  if (g->residual && (!g->out_fp32 || g->epilogue != DIG_EPI_LINEAR || (g->ldr * 4) % 16 || ((uintptr_t)g->residual & 15))) return false;
+  return true;
+}
+
+}  // namespace dig
