@@ -70,7 +70,9 @@ def test_gemm_fused_epilogues(ops):
     ops.gemm(a, wt, dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=pre, colsum=cs)
     refb = acc * x.grad
     assert torch.allclose(dh.float(), refb, atol=3e-2, rtol=1e-2)
-    assert torch.allclose(cs, refb.sum(0), atol=2e-2, rtol=1e-3)
+    # the fused bias gradient sums the bf16-rounded dh tile that is staged for the TMA store (as autocast's autograd would)
+    assert torch.allclose(cs, dh.float().sum(0), atol=2e-2, rtol=1e-4)
+    assert torch.allclose(cs, refb.sum(0), atol=0.15, rtol=2e-3)
     # ReLU mask
     act = torch.relu(rnd(M, N)).to(torch.bfloat16)
     o2 = torch.empty(M, N, device="cuda")
