@@ -80,26 +80,140 @@ __device__ __forceinline__ float erf_fast(float x) {
   q = fmaf(q, t, 1.0f);
   return __fdividef(x * p, q);
 }
-// exact-form (erf) GELU and its derivative, fp32 (nn.GELU, F:55)
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP, no range fix-up (denominators below are in [1, 1e3])
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exact-form (erf) GELU and its derivative, fp32 (nn.GELU, F:55).
+// gelu(x) = x (0.5 + xc P(xc^2) / Q(xc^2)), xc = clamp(x, +-3.925 sqrt 2): the erf_fast rational with the 1/sqrt(2) argument scale and the
+// factor 0.5 folded into the coefficients (12 FMA-pipe ops + 2 min/max + 1 MUFU per element).
+#define DIG_GELU_CLAMP 5.5507882f
+#define DIG_GELU_P0 3.989422482e-01f
+#define DIG_GELU_P1 3.372429997e-02f
+#define DIG_GELU_P2 4.667773067e-03f
+#define DIG_GELU_P3 1.673314111e-04f
+#define DIG_GELU_P4 6.324187753e-06f
+#define DIG_GELU_P5 2.273222238e-08f
+#define DIG_GELU_Q1 2.512003696e-01f
+#define DIG_GELU_Q2 2.856824797e-02f
+#define DIG_GELU_Q3 1.875976298e-03f
+#define DIG_GELU_Q4 7.307883344e-05f
+#define DIG_GELU_Q5 1.194982755e-06f
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float xc = fminf(fmaxf(x, -DIG_GELU_CLAMP), DIG_GELU_CLAMP);
+  const float t = xc * xc;
+  float p = DIG_GELU_P5;
+  p = fmaf(p, t, DIG_GELU_P4);
+  p = fmaf(p, t, DIG_GELU_P3);
+  p = fmaf(p, t, DIG_GELU_P2);
+  p = fmaf(p, t, DIG_GELU_P1);
+  p = fmaf(p, t, DIG_GELU_P0);
+  float q = DIG_GELU_Q5;
+  q = fmaf(q, t, DIG_GELU_Q4);
+  q = fmaf(q, t, DIG_GELU_Q3);
+  q = fmaf(q, t, DIG_GELU_Q2);
+  q = fmaf(q, t, DIG_GELU_Q1);
+  q = fmaf(q, t, 1.0f);
+  return x * fmaf(xc * p, rcp_approx(q), 0.5f);
+}
 // d/dx gelu_erf(x) = Phi(x) + x phi(x) = 0.5 + x P(x^2) / Q(x^2) on |x| <= 6 (clamped beyond; the odd part saturates at 0.5),
 // max abs error 3.9e-7 in fp32 against the closed form: one MUFU + 12 FMA instead of erf + exp.
+#define DIG_GELUG_P0 7.978851765e-01f
+#define DIG_GELUG_P1 -3.087451237e-02f
+#define DIG_GELUG_P2 1.421916872e-02f
+#define DIG_GELUG_P3 2.167418626e-05f
+#define DIG_GELUG_P4 3.587825389e-05f
+#define DIG_GELUG_P5 1.916786770e-07f
+#define DIG_GELUG_Q1 2.946448083e-01f
+#define DIG_GELUG_Q2 4.101880957e-02f
+#define DIG_GELUG_Q3 3.525759290e-03f
+#define DIG_GELUG_Q4 1.926611686e-04f
+#define DIG_GELUG_Q5 8.911869432e-06f
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   x = fminf(fmaxf(x, -6.0f), 6.0f);
   const float t = x * x;
-  float p = 1.916786770e-07f;
-  p = fmaf(p, t, 3.587825389e-05f);
-  p = fmaf(p, t, 2.167418626e-05f);
-  p = fmaf(p, t, 1.421916872e-02f);
-  p = fmaf(p, t, -3.087451237e-02f);
-  p = fmaf(p, t, 7.978851765e-01f);
-  float q = 8.911869432e-06f;
-  q = fmaf(q, t, 1.926611686e-04f);
-  q = fmaf(q, t, 3.525759290e-03f);
-  q = fmaf(q, t, 4.101880957e-02f);
-  q = fmaf(q, t, 2.946448083e-01f);
+  float p = DIG_GELUG_P5;
+  p = fmaf(p, t, DIG_GELUG_P4);
+  p = fmaf(p, t, DIG_GELUG_P3);
+  p = fmaf(p, t, DIG_GELUG_P2);
+  p = fmaf(p, t, DIG_GELUG_P1);
+  p = fmaf(p, t, DIG_GELUG_P0);
+  float q = DIG_GELUG_Q5;
+  q = fmaf(q, t, DIG_GELUG_Q4);
+  q = fmaf(q, t, DIG_GELUG_Q3);
+  q = fmaf(q, t, DIG_GELUG_Q2);
+  q = fmaf(q, t, DIG_GELUG_Q1);
   q = fmaf(q, t, 1.0f);
-  return 0.5f + __fdividef(x * p, q);
+  return fmaf(x * p, rcp_approx(q), 0.5f);
+}
+
+// ---- the same two functions on PAIRS of values with sm_100's packed fp32 instructions (FFMA2 / FMUL2 / FADD2): half the issue slots
+// of the scalar forms for the polynomial part.  Used by the GEMM epilogues, which are issue-bound.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+#define DIG_F2C(c) f2_pack(c, c)
+// (g0, g1) = gelu(x0, x1)
+__device__ __forceinline__ void gelu_erf_x2(float x0, float x1, float& g0, float& g1) {
+  const float c0 = fminf(fmaxf(x0, -DIG_GELU_CLAMP), DIG_GELU_CLAMP);
+  const float c1 = fminf(fmaxf(x1, -DIG_GELU_CLAMP), DIG_GELU_CLAMP);
+  const f32x2_t xc = f2_pack(c0, c1);
+  const f32x2_t t = f2_mul(xc, xc);
+  f32x2_t p = f2_fma(DIG_F2C(DIG_GELU_P5), t, DIG_F2C(DIG_GELU_P4));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELU_P3));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELU_P2));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELU_P1));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELU_P0));
+  f32x2_t q = f2_fma(DIG_F2C(DIG_GELU_Q5), t, DIG_F2C(DIG_GELU_Q4));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELU_Q3));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELU_Q2));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELU_Q1));
+  q = f2_fma(q, t, DIG_F2C(1.0f));
+  float q0, q1;
+  f2_unpack(q, q0, q1);
+  const f32x2_t w = f2_fma(f2_mul(xc, p), f2_pack(rcp_approx(q0), rcp_approx(q1)), DIG_F2C(0.5f));
+  f2_unpack(f2_mul(f2_pack(x0, x1), w), g0, g1);
+}
+// (d0, d1) *= gelu'(x0, x1)
+__device__ __forceinline__ void gelu_erf_grad_mul_x2(float x0, float x1, float& d0, float& d1) {
+  x0 = fminf(fmaxf(x0, -6.0f), 6.0f);
+  x1 = fminf(fmaxf(x1, -6.0f), 6.0f);
+  const f32x2_t x = f2_pack(x0, x1);
+  const f32x2_t t = f2_mul(x, x);
+  f32x2_t p = f2_fma(DIG_F2C(DIG_GELUG_P5), t, DIG_F2C(DIG_GELUG_P4));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P3));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P2));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P1));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P0));
+  f32x2_t q = f2_fma(DIG_F2C(DIG_GELUG_Q5), t, DIG_F2C(DIG_GELUG_Q4));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELUG_Q3));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELUG_Q2));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELUG_Q1));
+  q = f2_fma(q, t, DIG_F2C(1.0f));
+  float q0, q1;
+  f2_unpack(q, q0, q1);
+  const f32x2_t w = f2_fma(f2_mul(x, p), f2_pack(rcp_approx(q0), rcp_approx(q1)), DIG_F2C(0.5f));
+  f2_unpack(f2_mul(f2_pack(d0, d1), w), d0, d1);
 }
 
 // ------------------------------------------------------------------------------------------------

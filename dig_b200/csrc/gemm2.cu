@@ -339,12 +339,14 @@ int gemm2_try(const dig_gemm_t* g, cudaStream_t s) {
   else return 1;
   const long long split = g->split_k > 1 ? g->split_k : 1;
   if (m_tiles * ((g->N + bn - 1) / bn) * split < 32) return 1;
-  // Measured on B200 (scripts/gemm_dbg.py, gemm_dbg2.py): with the TMA-staged epilogue the 2-CTA kernel wins or ties everywhere except
-  // the erf-GELU forward epilogue, which is issue-bound and overlaps better with the 1-CTA kernel's smaller tiles, and split-K, where
-  // the 1-CTA kernel spreads the K slices over more CTAs.  DIG_GEMM_2CTA_MINK raises the K threshold for experiments.
+  // Measured on B200 (scripts/gemm_ab.py): with the TMA-staged epilogue the 2-CTA kernel wins or ties everywhere (erf-GELU forward:
+  // 110 us vs 130 us at 65536 x 1536 x 384 once the epilogue arithmetic is packed FFMA2) except split-K, where the 1-CTA kernel spreads
+  // the K slices over more CTAs.  DIG_GEMM_2CTA_MINK raises the K threshold, DIG_GEMM_2CTA_GELU=0 sends GELU back to 1-CTA (experiments).
   static int min_k = -1;
   if (min_k < 0) { const char* e = getenv("DIG_GEMM_2CTA_MINK"); min_k = e ? atoi(e) : 0; }
-  if (g->K < min_k || split > 1 || g->epilogue == DIG_EPI_GELU) return 1;
+  static int gelu_2cta = -1;
+  if (gelu_2cta < 0) { const char* e = getenv("DIG_GEMM_2CTA_GELU"); gelu_2cta = e ? atoi(e) : 1; }
+  if (g->K < min_k || split > 1 || (g->epilogue == DIG_EPI_GELU && !gelu_2cta)) return 1;
   if (bn == 256) return dispatch2<256>(g, s);
   if (bn == 192) return dispatch2<192>(g, s);
   return dispatch2<128>(g, s);

@@ -12,6 +12,10 @@
 
 #include "gemm_epilogue.cuh"
 
+#ifndef DIG_GELU_PACKED
+#define DIG_GELU_PACKED 1   // 0: scalar FFMA GELU in the epilogues (A/B switch)
+#endif
+
 namespace dig {
 
 static constexpr int kStageTileBytes = 4096;                       // 32 rows x 128 B
@@ -148,30 +152,50 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
         sts_f4(a, f);
       }
     } else {
-      // 8 units of 8 bf16 columns
+      // 8 units of 8 bf16 columns; the arithmetic runs on fp32 pairs (FADD2 / FFMA2), which halves the issue slots of this issue-bound loop
+      const bool scaled = alpha != 1.0f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]) * alpha;
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+        if (scaled) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] *= alpha;
+        }
         if (ep.bias != nullptr && gcol + 8 * j < N) {
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 8 * j));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 8 * j + 4));
-          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          f2_unpack(f2_add(f2_pack(f[0], f[1]), f2_pack(b0.x, b0.y)), f[0], f[1]);
+          f2_unpack(f2_add(f2_pack(f[2], f[3]), f2_pack(b0.z, b0.w)), f[2], f[3]);
+          f2_unpack(f2_add(f2_pack(f[4], f[5]), f2_pack(b1.x, b1.y)), f[4], f[5]);
+          f2_unpack(f2_add(f2_pack(f[6], f[7]), f2_pack(b1.z, b1.w)), f[6], f[7]);
         }
         const uint32_t off = row_s + (((uint32_t)j ^ sw) << 4);
         if (MODE == DIG_EPI_GELU) {
           sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+#if DIG_GELU_PACKED
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) gelu_erf_x2(f[e], f[e + 1], f[e], f[e + 1]);
+#else
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+#endif
           sts_u4(buf2 + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
         } else {
           if (MODE == DIG_EPI_GELU_BWD) {
             const uint4 x = lds_u4(buf + off);
+#if DIG_GELU_PACKED
+            gelu_erf_grad_mul_x2(bf16_lo(x.x), bf16_hi(x.x), f[0], f[1]);
+            gelu_erf_grad_mul_x2(bf16_lo(x.y), bf16_hi(x.y), f[2], f[3]);
+            gelu_erf_grad_mul_x2(bf16_lo(x.z), bf16_hi(x.z), f[4], f[5]);
+            gelu_erf_grad_mul_x2(bf16_lo(x.w), bf16_hi(x.w), f[6], f[7]);
+#else
             f[0] *= gelu_erf_grad(bf16_lo(x.x)); f[1] *= gelu_erf_grad(bf16_hi(x.x));
             f[2] *= gelu_erf_grad(bf16_lo(x.y)); f[3] *= gelu_erf_grad(bf16_hi(x.y));
             f[4] *= gelu_erf_grad(bf16_lo(x.z)); f[5] *= gelu_erf_grad(bf16_hi(x.z));
             f[6] *= gelu_erf_grad(bf16_lo(x.w)); f[7] *= gelu_erf_grad(bf16_hi(x.w));
+#endif
           }
           sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
         }

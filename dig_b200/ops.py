@@ -18,7 +18,8 @@ class DigError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    """In-tree library; DIG_B200_LIB names an alternative build (A/B experiments, scripts/build_variant.py)."""
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), os.environ.get("DIG_B200_LIB", _LIB_NAME))
 
 
 class _Gemm(ctypes.Structure):

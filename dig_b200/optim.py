@@ -23,6 +23,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._table = None
         self._sig = None
         self._step_count = 0
+        self._hyper_sig = None
         self._pending = (1.0, None, 0.0)   # (grad_scale, sumsq tensor, max_norm) set by the loss scaler for the next step
 
     def set_grad_transform(self, grad_scale=1.0, sumsq=None, max_norm=0.0):
@@ -41,6 +42,7 @@ class FusedAdamW(torch.optim.Optimizer):
                               [self.state[p]["exp_avg_sq"] for p, _ in entries])
         self._hyper_host = torch.empty(2, len(entries), dtype=torch.float32).pin_memory()
         self._hyper_dev = torch.empty(2, len(entries), dtype=torch.float32, device=dev)
+        self._hyper_sig = None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -60,17 +62,22 @@ class FusedAdamW(torch.optim.Optimizer):
         beta1, beta2 = entries[0][1]["betas"]
         eps = entries[0][1]["eps"]
         steps = set()
-        for i, (p, g) in enumerate(entries):
+        lrs, wds = [], []
+        for p, g in entries:
             if g["betas"] != (beta1, beta2) or g["eps"] != eps:
                 raise ops.DigError("FusedAdamW needs the same betas/eps in every param group")
-            self._hyper_host[0, i] = g["lr"]
-            self._hyper_host[1, i] = g["weight_decay"]
+            lrs.append(g["lr"])
+            wds.append(g["weight_decay"])
             st = self.state[p]
             st["step"] += 1
             steps.add(int(st["step"]))
         if len(steps) != 1:
             raise ops.DigError("FusedAdamW needs every parameter at the same step count")
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        hyper = (tuple(lrs), tuple(wds))
+        if hyper != self._hyper_sig:     # per-tensor lr / weight decay: one pinned staging write + one async H2D, only when they change
+            self._hyper_host.copy_(torch.tensor([lrs, wds], dtype=torch.float32))
+            self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_sig = hyper
         gs, sumsq, max_norm = self._pending
         t = self._table
         lib = ops.load()

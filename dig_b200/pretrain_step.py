@@ -101,6 +101,7 @@ class PretrainStep:
         self._build_shadows()
         self.saved = None
         self._n_masked = {}
+        self._grad_flat = None
 
     # ------------------------------------------------------------------ parameter bookkeeping
     def _signature(self):
@@ -462,7 +463,18 @@ class PretrainStep:
             raise ops.DigError("backward called without a saved forward")
         d, Bsz = self.d, sv["Bsz"]
         S, M, half = 2 * Bsz, 2 * Bsz * TOK, Bsz * TOK
-        flat = torch.zeros(self.grad_total, dtype=F32, device=self.device)
+        # One persistent flat gradient buffer: the views handed to autograd keep their addresses from step to step, so the pointer
+        # tables of the multi-tensor grad-norm / AdamW launches are built once (rebuilding them costs synchronous pageable H2D copies).
+        # If gradients of an earlier backward are still attached to the parameters (accumulation), they must not be overwritten.
+        p0 = self._named[self.train_names[0]]
+        if self._grad_flat is None:
+            self._grad_flat = torch.zeros(self.grad_total, dtype=F32, device=self.device)
+            flat = self._grad_flat
+        elif p0.grad is not None and p0.grad.data_ptr() == self._grad_flat.data_ptr():
+            flat = torch.zeros(self.grad_total, dtype=F32, device=self.device)
+        else:
+            flat = self._grad_flat
+            flat.zero_()
         grads = self._grad_views(flat)
         g = Bf.get("bw.g", (M, d), F32)
         S_ = self.shadow
