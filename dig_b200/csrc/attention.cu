@@ -9,6 +9,8 @@
 // Layout: qkv is the QKV projection output [S*256, 3*d] bf16 (q | k | v, each head a 64-column slice, exactly
 // the memory order F:93-95 reshapes); TMA pulls the per-head tiles straight out of it, so there is no
 // permute/contiguous pass.  The context is written as [S*256, d] bf16, ready for the output projection.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/dig_b200.h"
 
@@ -171,6 +173,194 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, persistent: one CTA per SM walks (sequence, head) items; two softmax warpgroups ("slots") own the two 128-query tiles
+// of an item and share its K/V.  Warp 0 = TMA producer (double-buffered Q/K/V, prefetches the next item while this one computes),
+// warp 1 = tcgen05.mma issuer and TMEM owner (2 x 256 columns: S -> P in place, O in the last 64 columns of the slot),
+// warps 2-5 = slot 0, warps 6-9 = slot 1 (a warp may only touch TMEM lanes 32*(warp%4)..+31; each slot covers all four quarters).
+// Per slot and item: S = Q K^T (MMA) -> row max / exp2 / sum, bf16 P back into TMEM (threads) -> O = P V (MMA, A from TMEM) ->
+// O / sum -> HBM (threads).  The tile-to-tile prologue, TMA latency and MMA latency of the one-shot kernel above are hidden behind the
+// other slot's softmax, which is the MUFU-bound critical resource.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kFwdPThreads = 320;
+static constexpr int kFwdPBuf = 98304;  // Q0 16K | Q1 16K | K 32K | V 32K
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__global__ void __launch_bounds__(kFwdPThreads, 1)
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int heads,
+                        float scale, int num_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFwdPBuf);
+  uint64_t* qk_full = bars + 0;    // [2 buffers] TMA -> MMA
+  uint64_t* v_full = bars + 2;     // [2 buffers] TMA -> MMA
+  uint64_t* kv_empty = bars + 4;   // [2 buffers] MMA -> TMA
+  uint64_t* s_full = bars + 6;     // [2 slots]   MMA -> softmax
+  uint64_t* p_full = bars + 8;     // [2 slots]   softmax -> MMA (128 arrivals)
+  uint64_t* o_full = bars + 10;    // [2 slots]   MMA -> softmax
+  uint64_t* s_free = bars + 12;    // [2 slots]   softmax -> MMA (128 arrivals): O drained, the slot's TMEM may be overwritten
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * kHd;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&s_free[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  constexpr uint32_t kColO = 192;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++n) {
+        const int b = n & 1;
+        const uint32_t u = (uint32_t)(n >> 1) & 1u;
+        const int head = w % heads, row0 = (w / heads) * kTok;
+        uint8_t* base = smem + b * kFwdPBuf;
+        mbar_wait(&kv_empty[b], u ^ 1u);
+        mbar_expect_tx(&qk_full[b], 65536);
+        tma_load_2d(base, &tm_qkv, &qk_full[b], head * kHd, row0);
+        tma_load_2d(base + 16384, &tm_qkv, &qk_full[b], head * kHd, row0 + 128);
+        tma_load_2d(base + 32768, &tm_qkv, &qk_full[b], d + head * kHd, row0);
+        tma_load_2d(base + 49152, &tm_qkv, &qk_full[b], d + head * kHd, row0 + 128);
+        mbar_expect_tx(&v_full[b], 32768);
+        tma_load_2d(base + 65536, &tm_qkv, &v_full[b], 2 * d + head * kHd, row0);
+        tma_load_2d(base + 81920, &tm_qkv, &v_full[b], 2 * d + head * kHd, row0 + 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+      int n = 0;
+      for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++n) {
+        const int b = n & 1;
+        const uint32_t u = (uint32_t)(n >> 1) & 1u, np = (uint32_t)n & 1u;
+        const uint32_t base = smem_u32(smem + b * kFwdPBuf);
+        mbar_wait(&qk_full[b], u);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&s_free[s], np ^ 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kHd / 16; ++k)
+            tc_mma_ss(tmem + s * 256, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024),
+                      make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s, k > 0);
+          tc_commit(&s_full[s]);
+        }
+        mbar_wait(&v_full[b], u);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&p_full[s], np);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kTok / 16; ++k)
+            tc_mma_ts(tmem + s * 256 + kColO, tmem + s * 256 + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0);
+          tc_commit(&o_full[s]);
+        }
+        tc_commit(&kv_empty[b]);  // both PV products have read V (and, before them, both S products Q and K)
+      }
+    }
+  } else {
+    const int s = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int t = quarter * 32 + lane;  // query row within the slot's 128-row tile == TMEM lane
+    const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * 256u;
+    const float sl2 = scale * kLog2e;
+    int n = 0;
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++n) {
+      const uint32_t np = (uint32_t)n & 1u;
+      const int head = w % heads, seq = w / heads;
+      mbar_wait(&s_full[s], np);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kTok; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tl + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      const float mb = mx * sl2;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kTok; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tl + c, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -mb));
+          sum0 += p0;
+          sum1 += p1;
+          pk[j >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st16(tl + (c >> 1), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[s]);
+
+      const float sum = sum0 + sum1;
+      const float inv = 1.0f / sum;
+      const long long grow = (long long)seq * kTok + s * 128 + t;
+      __nv_bfloat16* o = out + grow * d + head * kHd;
+      if (lse != nullptr) lse[((long long)seq * heads + head) * kTok + s * 128 + t] = mx * scale + logf(sum);
+      mbar_wait(&o_full[s], np);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kHd; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tl + kColO + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 p;
+          p.x = pack_bf16(__uint_as_float(v[j + 0]) * inv, __uint_as_float(v[j + 1]) * inv);
+          p.y = pack_bf16(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+          p.z = pack_bf16(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+          p.w = pack_bf16(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(o + c + j) = p;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free[s]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -398,7 +588,16 @@ extern "C" int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (int)(num_seqs * heads * 2);
-  if (!p_in_smem) {
+  static int one_shot = -1;  // DIG_ATTN_FWD_ONESHOT=1: the non-persistent kernel (A/B experiments)
+  if (one_shot < 0) { const char* e = getenv("DIG_ATTN_FWD_ONESHOT"); one_shot = (e && e[0] == '1') ? 1 : 0; }
+  if (!p_in_smem && !one_shot) {
+    const int smem = 2 * kFwdPBuf + 1024 + 256;
+    static bool set = false;
+    if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    const int items = (int)(num_seqs * heads);
+    const int ctas = items < num_sms() ? items : num_sms();
+    attn_fwd_persist_kernel<<<ctas, kFwdPThreads, smem, s>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), lse, heads, scale, items);
+  } else if (!p_in_smem) {
     const int smem = 81920 + 1024 + 128;
     static bool set = false;
     if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
