@@ -195,11 +195,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(kFwdPThreads, 1)
-attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int heads,
-                        float scale, int num_items) {
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
+                        int heads, float scale, int num_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFwdPBuf);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFwdPBuf + 2 * 16384);   // after the two 16 KB output staging tiles
   uint64_t* qk_full = bars + 0;    // [2 buffers] TMA -> MMA
   uint64_t* v_full = bars + 2;     // [2 buffers] TMA -> MMA
   uint64_t* kv_empty = bars + 4;   // [2 buffers] MMA -> TMA
@@ -214,6 +214,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_out);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qk_full[i], 1);
       mbar_init(&v_full[i], 1);
@@ -292,38 +293,61 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
     const int t = quarter * 32 + lane;  // query row within the slot's 128-row tile == TMEM lane
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * 256u;
     const float sl2 = scale * kLog2e;
+    const uint32_t stage_s = smem_u32(smem + 2 * kFwdPBuf + s * 16384);
     int n = 0;
     for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++n) {
       const uint32_t np = (uint32_t)n & 1u;
       const int head = w % heads, seq = w / heads;
       mbar_wait(&s_full[s], np);
       tc_fence_after();
+      // both passes keep one TMEM load in flight behind the chunk being processed (two register buffers)
       float mx = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(tl, va);
 #pragma unroll 1
-      for (int c = 0; c < kTok; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tl + c, v);
-        tmem_ld_wait();
+        for (int c = 0; c < kTok; c += 64) {
+          tmem_ld_wait();
+          tmem_ld32(tl + c + 32, vb);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
+          tmem_ld_wait();
+          if (c + 64 < kTok) tmem_ld32(tl + c + 64, va);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+        }
       }
       const float mb = mx * sl2;
       float sum0 = 0.f, sum1 = 0.f;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(tl, va);
 #pragma unroll 1
-      for (int c = 0; c < kTok; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tl + c, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < kTok; c += 64) {
+          uint32_t pk[16];
+          tmem_ld_wait();
+          tmem_ld32(tl + c + 32, vb);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl2, -mb));
-          sum0 += p0;
-          sum1 += p1;
-          pk[j >> 1] = pack_bf16(p0, p1);
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(va[j]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(va[j + 1]), sl2, -mb));
+            sum0 += p0;
+            sum1 += p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_ld_wait();   // vb has landed: the S columns the next two P stores overwrite (c/2.., <= c+31) have been read
+          if (c + 64 < kTok) tmem_ld32(tl + c + 64, va);
+          tmem_st16(tl + (c >> 1), pk);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[j]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[j + 1]), sl2, -mb));
+            sum0 += p0;
+            sum1 += p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st16(tl + ((c + 32) >> 1), pk);
         }
-        tmem_st16(tl + (c >> 1), pk);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -331,11 +355,14 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
 
       const float sum = sum0 + sum1;
       const float inv = 1.0f / sum;
-      const long long grow = (long long)seq * kTok + s * 128 + t;
-      __nv_bfloat16* o = out + grow * d + head * kHd;
       if (lse != nullptr) lse[((long long)seq * heads + head) * kTok + s * 128 + t] = mx * scale + logf(sum);
       mbar_wait(&o_full[s], np);
       tc_fence_after();
+      // O / sum goes out through a 128 x 64 bf16 swizzled staging tile and ONE TMA store per slot and item: a row-per-thread
+      // STG.128 touches 32 different lines per warp instruction (32 LSU wavefronts), which made the store the longest stall of the
+      // first version of this kernel.
+      if (t == 0) tma_store_wait_read_all();                 // last item's store has finished reading the staging tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
 #pragma unroll
       for (int c = 0; c < kHd; c += 32) {
         uint32_t v[32];
@@ -348,12 +375,19 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
           p.y = pack_bf16(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
           p.z = pack_bf16(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
           p.w = pack_bf16(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(o + c + j) = p;
+          sts_u4(stage_s + sw128_offset((uint32_t)t, (uint32_t)((c + j) >> 3)), p);
         }
       }
       tc_fence_before();
       mbar_arrive(&s_free[s]);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
+      if (t == 0) {
+        tma_store_2d(&tm_out, stage_s, head * kHd, seq * kTok + s * 128);
+        tma_store_commit();
+      }
     }
+    if (t == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -591,12 +625,15 @@ extern "C" int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t
   static int one_shot = -1;  // DIG_ATTN_FWD_ONESHOT=1: the non-persistent kernel (A/B experiments)
   if (one_shot < 0) { const char* e = getenv("DIG_ATTN_FWD_ONESHOT"); one_shot = (e && e[0] == '1') ? 1 : 0; }
   if (!p_in_smem && !one_shot) {
-    const int smem = 2 * kFwdPBuf + 1024 + 256;
+    const int smem = 2 * kFwdPBuf + 2 * 16384 + 1024 + 256;
+    CUtensorMap to;
+    rc = make_tmap_bf16_2d(&to, out, (uint64_t)num_seqs * kTok, (uint64_t)d, (uint64_t)d, 128, 64);
+    if (rc) return rc;
     static bool set = false;
     if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
     const int items = (int)(num_seqs * heads);
     const int ctas = items < num_sms() ? items : num_sms();
-    attn_fwd_persist_kernel<<<ctas, kFwdPThreads, smem, s>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), lse, heads, scale, items);
+    attn_fwd_persist_kernel<<<ctas, kFwdPThreads, smem, s>>>(tm, to, lse, heads, scale, items);
   } else if (!p_in_smem) {
     const int smem = 81920 + 1024 + 128;
     static bool set = false;

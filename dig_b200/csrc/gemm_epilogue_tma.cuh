@@ -21,21 +21,6 @@ namespace dig {
 static constexpr int kStageTileBytes = 4096;                       // 32 rows x 128 B
 static constexpr int kEpiTmaBytes = kEpiWarps * 2 * kStageTileBytes;  // two staging tiles per epilogue warp
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem, int c_inner, int c_outer) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(smem), "r"(c_inner), "r"(c_outer)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem, int c_inner, int c_outer) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem), "r"(c_inner), "r"(c_outer)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c_inner, int c_outer) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
