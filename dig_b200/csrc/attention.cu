@@ -185,7 +185,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 // O / sum -> HBM (threads).  The tile-to-tile prologue, TMA latency and MMA latency of the one-shot kernel above are hidden behind the
 // other slot's softmax, which is the MUFU-bound critical resource.
 // ------------------------------------------------------------------------------------------------
+#ifndef DIG_ATTN_EVT
+#define DIG_ATTN_EVT 1
+#endif
+#ifndef DIG_ATTN_STAGGER
+#define DIG_ATTN_STAGGER 3000
+#endif
+static constexpr long long kAttnStagger = DIG_ATTN_STAGGER;  // SM clocks between the first S products of slot 0 and slot 1
 static constexpr int kFwdPThreads = 320;
+
+// Bring-up instrumentation: when a buffer is registered (dig_attention_debug_buffer), CTA 0 records SM clock stamps of its MMA thread
+// and of one softmax thread per slot for the first 12 items (scripts/attn_timeline.py prints them).  Null in normal operation.
+__device__ long long* g_attn_dbg = nullptr;
+#define DIG_STAMP(role, n, k)                                                                         \
+  do {                                                                                                \
+    if (dbg != nullptr && (n) < 12) dbg[((role) * 12 + (n)) * 8 + (k)] = clock64();                     \
+  } while (0)
 static constexpr int kFwdPBuf = 98304;  // Q0 16K | Q1 16K | K 32K | V 32K
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -211,6 +226,13 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * kHd;
+  long long* const dbg = (blockIdx.x == 0 && lane == 0 && (warp == 1 || (warp & 3) == 0)) ? g_attn_dbg : nullptr;
+  if (dbg != nullptr && warp == 1) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    dbg[11 * 8 + 0] = clock64();
+    dbg[11 * 8 + 2] = (long long)gt;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -252,6 +274,62 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tma_load_2d(base + 81920, &tm_qkv, &v_full[b], 2 * d + head * kHd, row0 + 128);
       }
     }
+#if DIG_ATTN_EVT
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // Event-driven issue: each slot is its own S -> (softmax) -> PV pipeline.  The thread probes (mbarrier.test_wait, non-blocking)
+      // the barriers the slot's next action needs and issues whichever is ready, and slot 1 is started half a period late, so one
+      // slot's MMAs, O drain and barrier round trips hide behind the other slot's exp2 work instead of both slots hitting the MUFU
+      // pipe -- and then both leaving it -- together (measured with the clock stamps: 48% MUFU duty in lock-step).
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+      const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      int cnt[2] = {0, 0};      // items completed (PV issued) per slot
+      int stage[2] = {0, 0};    // 0: S to issue, 1: PV to issue
+      int pv_issued[2] = {0, 0};  // per K/V buffer: slots whose PV of the buffer's current item has been issued
+      bool first_s0 = false;
+      long long t_first = 0;
+      while (cnt[0] < my_items || cnt[1] < my_items) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int n = cnt[s];
+          if (n >= my_items) continue;
+          const int b = n & 1;
+          const uint32_t u = (uint32_t)(n >> 1) & 1u, np = (uint32_t)n & 1u;
+          const uint32_t base = smem_u32(smem + b * kFwdPBuf);
+          if (stage[s] == 0) {
+            if (!mbar_test_wait(&qk_full[b], u) || !mbar_test_wait(&s_free[s], np ^ 1u)) continue;
+            if (s == 1 && n == 0 && !first_s0) continue;                                   // slot 0 leads ...
+            if (s == 1 && n == 0 && clock64() - t_first < kAttnStagger) continue;          // ... by about half a slot period
+            if (s == 0 && n == 0) { first_s0 = true; t_first = clock64(); }
+            tc_fence_after();
+            DIG_STAMP(0, n, 1 + s);
+#pragma unroll
+            for (int k = 0; k < kHd / 16; ++k)
+              tc_mma_ss(tmem + s * 256, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024),
+                        make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s, k > 0);
+            tc_commit(&s_full[s]);
+            stage[s] = 1;
+          } else {
+            if (!mbar_test_wait(&p_full[s], np) || !mbar_test_wait(&v_full[b], u)) continue;
+            tc_fence_after();
+            DIG_STAMP(0, n, 4 + s);
+#pragma unroll
+            for (int k = 0; k < kTok / 16; ++k)
+              tc_mma_ts(tmem + s * 256 + kColO, tmem + s * 256 + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o,
+                        k > 0);
+            tc_commit(&o_full[s]);
+            if (++pv_issued[b] == 2) {  // both slots are through with this item's Q/K/V: hand the buffer back to the producer
+              tc_commit(&kv_empty[b]);
+              pv_issued[b] = 0;
+            }
+            stage[s] = 0;
+            cnt[s] = n + 1;
+          }
+        }
+      }
+    }
+#else
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
@@ -263,30 +341,36 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const uint32_t base = smem_u32(smem + b * kFwdPBuf);
         mbar_wait(&qk_full[b], u);
         tc_fence_after();
+        DIG_STAMP(0, n, 0);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           mbar_wait(&s_free[s], np ^ 1u);
           tc_fence_after();
+          DIG_STAMP(0, n, 1 + s);
 #pragma unroll
           for (int k = 0; k < kHd / 16; ++k)
             tc_mma_ss(tmem + s * 256, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024),
                       make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s, k > 0);
           tc_commit(&s_full[s]);
         }
+        DIG_STAMP(0, n, 3);
         mbar_wait(&v_full[b], u);
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           mbar_wait(&p_full[s], np);
           tc_fence_after();
+          DIG_STAMP(0, n, 4 + s);
 #pragma unroll
           for (int k = 0; k < kTok / 16; ++k)
             tc_mma_ts(tmem + s * 256 + kColO, tmem + s * 256 + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0);
           tc_commit(&o_full[s]);
         }
         tc_commit(&kv_empty[b]);  // both PV products have read V (and, before them, both S products Q and K)
+        DIG_STAMP(0, n, 6);
       }
     }
+#endif
   } else {
     const int s = (warp - 2) >> 2;
     const int quarter = warp & 3;
@@ -298,8 +382,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++n) {
       const uint32_t np = (uint32_t)n & 1u;
       const int head = w % heads, seq = w / heads;
+      DIG_STAMP(1 + s, n, 0);
       mbar_wait(&s_full[s], np);
       tc_fence_after();
+      DIG_STAMP(1 + s, n, 1);
       // both passes keep one TMEM load in flight behind the chunk being processed (two register buffers)
       float mx = -INFINITY;
       {
@@ -318,6 +404,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
       const float mb = mx * sl2;
+      DIG_STAMP(1 + s, n, 2);
       float sum0 = 0.f, sum1 = 0.f;
       {
         uint32_t va[32], vb[32];
@@ -349,15 +436,18 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           tmem_st16(tl + ((c + 32) >> 1), pk);
         }
       }
+      DIG_STAMP(1 + s, n, 3);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[s]);
+      DIG_STAMP(1 + s, n, 4);
 
       const float sum = sum0 + sum1;
       const float inv = 1.0f / sum;
       if (lse != nullptr) lse[((long long)seq * heads + head) * kTok + s * 128 + t] = mx * scale + logf(sum);
       mbar_wait(&o_full[s], np);
       tc_fence_after();
+      DIG_STAMP(1 + s, n, 5);
       // O / sum goes out through a 128 x 64 bf16 swizzled staging tile and ONE TMA store per slot and item: a row-per-thread
       // STG.128 touches 32 different lines per warp instruction (32 LSU wavefronts), which made the store the longest stall of the
       // first version of this kernel.
@@ -380,18 +470,26 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       }
       tc_fence_before();
       mbar_arrive(&s_free[s]);
+      DIG_STAMP(1 + s, n, 6);
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
       if (t == 0) {
         tma_store_2d(&tm_out, stage_s, head * kHd, seq * kTok + s * 128);
         tma_store_commit();
       }
+      DIG_STAMP(1 + s, n, 7);
     }
     if (t == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (dbg != nullptr && warp == 1) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    dbg[11 * 8 + 1] = clock64();
+    dbg[11 * 8 + 3] = (long long)gt;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -610,6 +708,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 }
 
 }  // namespace dig
+
+// bring-up only (not part of include/dig_b200.h): device buffer of 3 x 12 x 8 int64 clock stamps, or NULL to switch recording off
+extern "C" int dig_attention_debug_buffer(void* buf) {
+  long long* p = reinterpret_cast<long long*>(buf);
+  return cudaMemcpyToSymbol(dig::g_attn_dbg, &p, sizeof(p)) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t num_seqs, int32_t heads, float scale,
                                  int32_t p_in_smem, void* stream) {

@@ -1,0 +1,30 @@
+"""Clock-stamp timeline of CTA 0 of the persistent attention forward (bring-up instrumentation in attention.cu)."""
+import ctypes, sys, torch
+sys.path.insert(0, ".")
+from dig_b200 import ops
+lib = ops.load()
+S, h = 256, 6
+d, scale = h * 64, 64 ** -0.5
+qkv = (torch.randn(S * 256, 3 * d, device="cuda") * 1.5).bfloat16()
+out = torch.empty(S * 256, d, device="cuda", dtype=torch.bfloat16); lse = torch.empty(S, h, 256, device="cuda")
+for _ in range(3): ops.attention_fwd(qkv, out, lse, h, scale)
+buf = torch.zeros(3, 12, 8, dtype=torch.int64, device="cuda")
+lib.dig_attention_debug_buffer.argtypes = [ctypes.c_void_p]
+lib.dig_attention_debug_buffer(ctypes.c_void_p(buf.data_ptr()))
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record(); ops.attention_fwd(qkv, out, lse, h, scale); e1.record()
+torch.cuda.synchronize()
+print('kernel (events): %.1f us' % (e0.elapsed_time(e1) * 1e3))
+lib.dig_attention_debug_buffer(None)
+b = buf.cpu()
+k = b[0, 11]
+print('CTA 0: %d clocks in %d ns -> %.3f GHz' % (k[1] - k[0], k[3] - k[2], float(k[1] - k[0]) / float(k[3] - k[2])))
+b[0, 11] = 0
+t0 = int(b[b > 0].min())
+names = ["MMA  : qk_full | s_free0 | s_free1 | S issued | p_full0 | p_full1 | PV issued",
+         "slot0: loop top | s_full | pass1 done | pass2 done | p arrive | o_full | s_free arrive | stored",
+         "slot1: (same)"]
+for r in range(3):
+    print(names[r])
+    for n in range(11):
+        print("   item %2d: " % n + " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[r, n]))

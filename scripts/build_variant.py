@@ -7,7 +7,7 @@ name, extra = sys.argv[1], sys.argv[2:]
 srcs = sorted(glob.glob(os.path.join(ROOT, "dig_b200", "csrc", "*.cu")))
 od = os.path.join(ROOT, "build", "variant_" + name)
 os.makedirs(od, exist_ok=True)
-flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"] + extra
+flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"] + extra
 objs = [os.path.join(od, os.path.basename(s)[:-3] + ".o") for s in srcs]
 def cc(so):
     subprocess.run(["nvcc"] + flags + ["-c", "-o", so[1], so[0]], check=True)
