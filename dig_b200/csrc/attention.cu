@@ -502,16 +502,15 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 //   dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j   (TMEM accumulators)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(160, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                __nv_bfloat16* __restrict__ dqkv, int heads, float scale) {
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_o,
+                const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse, int heads, float scale) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;            // 256 x 64, rows = tokens (two 128-row tiles of 16 KB)
   uint8_t* sK = smem + 32768;
   uint8_t* sV = smem + 65536;
   uint8_t* sdO = smem + 98304;
-  uint8_t* sP = smem + 131072;   // [128 queries x 128 keys] as two 64-key column chunks of 16 KB
+  uint8_t* sP = smem + 131072;   // [128 queries x 128 keys] as two 64-key column chunks of 16 KB; first the O tiles (for D), last dQ staging
   uint8_t* sdS = smem + 163840;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 196608);
   uint64_t* bar_ld = bars + 0;
@@ -525,11 +524,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const int seq = blockIdx.x / heads;
   const int d = heads * kHd;
   const int row0 = seq * kTok;
+  long long* const dbg = (blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 0)) ? g_attn_dbg : nullptr;
+  DIG_STAMP(warp == 4 ? 0 : 1, 0, 0);
 
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_do);
+      tma_prefetch_desc(&tm_o);
+      tma_prefetch_desc(&tm_dqkv);
       mbar_init(bar_ld, 1);
       mbar_init(bar_sdp, 1);
       mbar_init(bar_pds, 128);
@@ -547,16 +550,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_expect_tx(bar_ld, 4 * 32768);
+      mbar_expect_tx(bar_ld, 5 * 32768);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
+        tma_load_2d(sdO + r * 16384, &tm_do, bar_ld, head * kHd, row0 + r * 128);
+        tma_load_2d(sP + r * 16384, &tm_o, bar_ld, head * kHd, row0 + r * 128);      // O rides in the P buffer until D is computed
         tma_load_2d(sQ + r * 16384, &tm_qkv, bar_ld, head * kHd, row0 + r * 128);
         tma_load_2d(sK + r * 16384, &tm_qkv, bar_ld, d + head * kHd, row0 + r * 128);
         tma_load_2d(sV + r * 16384, &tm_qkv, bar_ld, 2 * d + head * kHd, row0 + r * 128);
-        tma_load_2d(sdO + r * 16384, &tm_do, bar_ld, head * kHd, row0 + r * 128);
       }
+      DIG_STAMP(0, 0, 1);
       mbar_wait(bar_ld, 0);
       tc_fence_after();
+      DIG_STAMP(0, 0, 2);
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, false, false);
       constexpr uint32_t id_tt = make_idesc_bf16(128, 64, true, true);   // dV, dK: A = P^T / dS^T (MN-major), B MN-major
       constexpr uint32_t id_q = make_idesc_bf16(128, 64, false, true);   // dQ: A = dS (K-major), B = K (MN-major)
@@ -574,8 +580,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             tc_mma_ss(tmem + cdP, make_sdesc_sw128(adO + i * 16384 + k * 32, 16, 1024), make_sdesc_sw128(aV + j * 16384 + k * 32, 16, 1024),
                       id_s, k > 0);
           tc_commit(bar_sdp);
+          DIG_STAMP(0, 1 + it, 0);
           mbar_wait(bar_pds, it & 1);
           tc_fence_after();
+          DIG_STAMP(0, 1 + it, 1);
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
             tc_mma_ss(tmem + cdV, make_sdesc_sw128(aP + k * 2048, 16384, 1024), make_sdesc_sw128(adO + i * 16384 + k * 2048, 8192, 1024),
@@ -589,6 +597,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             tc_mma_ss(tmem + cdQ + i * 64, make_sdesc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                       make_sdesc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0));
           tc_commit(bar_mma);
+          DIG_STAMP(0, 1 + it, 2);
         }
       }
     }
@@ -596,31 +605,58 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int t = threadIdx.x;  // row within a 128-token tile == TMEM lane
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
     const float sl2 = scale * kLog2e;
-    // D_i = rowsum(dO o O), lse_i for the two query rows this thread owns
+    const uint32_t sP_s = smem_u32(sP), sdS_s = smem_u32(sdS), sdO_s = smem_u32(sdO);
+    // 128 x 64 fp32 accumulator rows (this thread's lane) -> bf16, times `mul`, into a swizzled staging tile for one TMA store
+    auto stage_tile = [&](uint32_t tcol, uint32_t dst_s, float mul) {
+#pragma unroll
+      for (int c = 0; c < kHd; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tl + tcol + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          uint4 p;
+          p.x = pack_bf16(__uint_as_float(v[q + 0]) * mul, __uint_as_float(v[q + 1]) * mul);
+          p.y = pack_bf16(__uint_as_float(v[q + 2]) * mul, __uint_as_float(v[q + 3]) * mul);
+          p.z = pack_bf16(__uint_as_float(v[q + 4]) * mul, __uint_as_float(v[q + 5]) * mul);
+          p.w = pack_bf16(__uint_as_float(v[q + 6]) * mul, __uint_as_float(v[q + 7]) * mul);
+          sts_u4(dst_s + sw128_offset((uint32_t)t, (uint32_t)((c + q) >> 3)), p);
+        }
+      }
+    };
+    // D_i = rowsum(dO o O) from the TMA-staged tiles (a row-per-thread global read costs 32 LSU wavefronts per instruction), lse_i
     float Dr[2], Lr[2];
 #pragma unroll
+    for (int i = 0; i < 2; ++i) Lr[i] = lse[((long long)seq * heads + head) * kTok + i * 128 + t] * kLog2e;
+    mbar_wait(bar_ld, 0);
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const long long grow = (long long)row0 + i * 128 + t;
-      const uint4* po = reinterpret_cast<const uint4*>(out + grow * d + head * kHd);
-      const uint4* pd = reinterpret_cast<const uint4*>(dout + grow * d + head * kHd);
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const uint4 a = __ldg(po + c), b = __ldg(pd + c);
+        const uint32_t off = (uint32_t)i * 16384u + sw128_offset((uint32_t)t, (uint32_t)c);
+        const uint4 a = lds_u4(sP_s + off), b = lds_u4(sdO_s + off);
         acc += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
                bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
       }
       Dr[i] = acc;
-      Lr[i] = lse[((long long)seq * heads + head) * kTok + i * 128 + t] * kLog2e;
     }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // every thread has read its O rows: the P buffer may be overwritten
     int mma_seen = 0;
     int it = 0;
-    const uint32_t sP_s = smem_u32(sP), sdS_s = smem_u32(sdS);
+    DIG_STAMP(1, 0, 1);
     for (int j = 0; j < 2; ++j) {
       for (int i = 0; i < 2; ++i, ++it) {
+        DIG_STAMP(1, 1 + it, 0);
         mbar_wait(bar_sdp, it & 1);
         tc_fence_after();
+        DIG_STAMP(1, 1 + it, 1);
         while (mma_seen < it) { mbar_wait(bar_mma, mma_seen & 1); ++mma_seen; }  // P/dS buffers free again
+        if (j == 1 && i == 0) {  // ... and so has the TMA store of dV_0 / dK_0 that was staged in them
+          if (t == 0) tma_store_wait_read_all();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        DIG_STAMP(1, 1 + it, 2);
 #pragma unroll 1
         for (int c = 0; c < 128; c += 32) {
           uint32_t s[32], g[32];
@@ -630,10 +666,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           uint32_t pp[16], ds[16];
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
-            const float p0 = exp2f(fmaf(__uint_as_float(s[q]), sl2, -Lr[i]));
-            const float p1 = exp2f(fmaf(__uint_as_float(s[q + 1]), sl2, -Lr[i]));
-            const float d0 = p0 * (__uint_as_float(g[q]) - Dr[i]) * scale;
-            const float d1 = p1 * (__uint_as_float(g[q + 1]) - Dr[i]) * scale;
+            // dS is kept unscaled here; `scale` is applied once per output element when dK and dQ leave TMEM
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[q]), sl2, -Lr[i]));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[q + 1]), sl2, -Lr[i]));
+            const float d0 = p0 * (__uint_as_float(g[q]) - Dr[i]);
+            const float d1 = p1 * (__uint_as_float(g[q + 1]) - Dr[i]);
             pp[q >> 1] = pack_bf16(p0, p1);
             ds[q >> 1] = pack_bf16(d0, d1);
           }
@@ -649,58 +686,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(bar_pds);
+        DIG_STAMP(1, 1 + it, 3);
         if (i == 1) {
           while (mma_seen < it + 1) { mbar_wait(bar_mma, mma_seen & 1); ++mma_seen; }
           tc_fence_after();
-          const long long grow = (long long)row0 + j * 128 + t;
-#pragma unroll
-          for (int which = 0; which < 2; ++which) {  // 0: dV, 1: dK
-            __nv_bfloat16* o = dqkv + grow * (3 * d) + (which == 0 ? 2 * d : d) + head * kHd;
-#pragma unroll
-            for (int c = 0; c < kHd; c += 32) {
-              uint32_t v[32];
-              tmem_ld32(tl + (which == 0 ? cdV : cdK) + c, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int q = 0; q < 32; q += 8) {
-                uint4 p;
-                p.x = pack_bf16(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1]));
-                p.y = pack_bf16(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
-                p.z = pack_bf16(__uint_as_float(v[q + 4]), __uint_as_float(v[q + 5]));
-                p.w = pack_bf16(__uint_as_float(v[q + 6]), __uint_as_float(v[q + 7]));
-                *reinterpret_cast<uint4*>(o + c + q) = p;
-              }
-            }
-          }
+          DIG_STAMP(1, 1 + it, 4);
+          // dV_j, dK_j: TMEM -> swizzled staging (the idle P / dS buffers) -> two TMA stores
+          stage_tile(cdV, sP_s, 1.0f);
+          stage_tile(cdK, sdS_s, scale);
           tc_fence_before();
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (t == 0) {
+            tma_store_2d(&tm_dqkv, sP_s, 2 * d + head * kHd, row0 + j * 128);
+            tma_store_2d(&tm_dqkv, sdS_s, d + head * kHd, row0 + j * 128);
+            tma_store_commit();
+          }
+          DIG_STAMP(1, 1 + it, 5);
         }
       }
     }
-    // dQ for both query tiles (complete after the last commit, which the i==1 wait above has seen)
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const long long grow = (long long)row0 + i * 128 + t;
-      __nv_bfloat16* o = dqkv + grow * (3 * d) + head * kHd;
-#pragma unroll
-      for (int c = 0; c < kHd; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tl + cdQ + i * 64 + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-          uint4 p;
-          p.x = pack_bf16(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1]));
-          p.y = pack_bf16(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
-          p.z = pack_bf16(__uint_as_float(v[q + 4]), __uint_as_float(v[q + 5]));
-          p.w = pack_bf16(__uint_as_float(v[q + 6]), __uint_as_float(v[q + 7]));
-          *reinterpret_cast<uint4*>(o + c + q) = p;
-        }
-      }
+    DIG_STAMP(1, 5, 0);
+    // dQ for both query tiles (complete after the last commit, which the i==1 wait above has seen); second halves of the staging buffers
+    stage_tile(cdQ, sP_s + 16384, scale);
+    stage_tile(cdQ + 64, sdS_s + 16384, scale);
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t == 0) {
+      tma_store_2d(&tm_dqkv, sP_s + 16384, head * kHd, row0);
+      tma_store_2d(&tm_dqkv, sdS_s + 16384, head * kHd, row0 + 128);
+      tma_store_commit();
+      tma_store_wait_all();
     }
   }
 
+  DIG_STAMP(warp == 4 ? 0 : 1, 5, 1);
   tc_fence_before();
   __syncthreads();
+  DIG_STAMP(warp == 4 ? 0 : 1, 5, 2);
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -759,18 +782,20 @@ extern "C" int dig_attention_bwd(const void* qkv, const void* out, const void* d
   DIG_REQUIRE(qkv && out && dout && lse && dqkv, "dig_attention_bwd: null pointer");
   DIG_REQUIRE(num_seqs > 0 && heads > 0, "dig_attention_bwd: empty problem");
   const int d = heads * kHd;
-  CUtensorMap tq, td;
+  CUtensorMap tq, td, to, tg;
   int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)num_seqs * kTok, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&td, dout, (uint64_t)num_seqs * kTok, (uint64_t)d, (uint64_t)d, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&to, out, (uint64_t)num_seqs * kTok, (uint64_t)d, (uint64_t)d, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tg, dqkv, (uint64_t)num_seqs * kTok, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64);
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int smem = 196608 + 1024 + 128;
   static bool set = false;
   if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-  attn_bwd_kernel<<<(int)(num_seqs * heads), 160, smem, s>>>(tq, td, reinterpret_cast<const __nv_bfloat16*>(out),
-                                                            reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-                                                            reinterpret_cast<__nv_bfloat16*>(dqkv), heads, scale);
+  attn_bwd_kernel<<<(int)(num_seqs * heads), 160, smem, s>>>(tq, td, to, tg, lse, heads, scale);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -393,6 +393,17 @@ __device__ __forceinline__ void red_shared_add_f32(uint32_t a, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
 // 128-byte swizzle: byte offset of (row, 16-byte chunk) inside a tile whose rows are 128 bytes wide
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
   return row * 128u + (((chunk16 ^ row) & 7u) << 4);

@@ -27,17 +27,6 @@ __device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, const CUtens
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-
 // Per-warp persistent state of the TMA epilogue (lives in registers across tiles).
 struct EpiTmaState {
   uint32_t stage_s;   // shared address of this warp's two staging tiles

@@ -28,3 +28,18 @@ for r in range(3):
     print(names[r])
     for n in range(11):
         print("   item %2d: " % n + " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[r, n]))
+
+# ---- backward (one-shot kernel): CTA 0 ----
+dout = torch.randn(S * 256, d, device="cuda").bfloat16(); dqkv = torch.empty_like(qkv)
+for _ in range(2): ops.attention_bwd(qkv, out, dout, lse, dqkv, h, scale)
+buf.zero_()
+lib.dig_attention_debug_buffer(ctypes.c_void_p(buf.data_ptr()))
+ops.attention_bwd(qkv, out, dout, lse, dqkv, h, scale)
+torch.cuda.synchronize()
+lib.dig_attention_debug_buffer(None)
+b = buf.cpu()
+t0 = int(b[b > 0].min())
+print("bwd MMA thread : row0 = start | loads issued | loads landed ; rows 1-4 (it): S,dP committed | pds seen | dV,dK,dQ committed ; row5: - | end | after sync")
+for n in range(6): print("   ", " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[0, n]))
+print("bwd thread 0   : row0 = start | D,lse done ; rows 1-4 (it): top | sdp seen | bufs free | pds arrive | mma seen | dV,dK stored ; row5: loop done | end | after sync")
+for n in range(6): print("   ", " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[1, n]))
