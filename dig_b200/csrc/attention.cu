@@ -501,7 +501,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 //   S = Q_i K_j^T, dP = dO_i V_j^T  (TMEM)  ->  P = exp(scale*S - lse), dS = scale * P o (dP - D)  (threads)
 //   dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j   (TMEM accumulators)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(160, 1)
+static constexpr int kBwdThreads = 288;  // warps 0-3: key columns 0-63 of a block, warps 4-7: columns 64-127 (same TMEM lane quarters), warp 8: TMA + MMA
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_o,
                 const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse, int heads, float scale) {
   extern __shared__ uint8_t smem_raw[];
@@ -524,10 +526,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const int seq = blockIdx.x / heads;
   const int d = heads * kHd;
   const int row0 = seq * kTok;
-  long long* const dbg = (blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 0)) ? g_attn_dbg : nullptr;
-  DIG_STAMP(warp == 4 ? 0 : 1, 0, 0);
+  long long* const dbg = (blockIdx.x == 0 && lane == 0 && (warp == 8 || warp == 0)) ? g_attn_dbg : nullptr;
+  DIG_STAMP(warp == 8 ? 0 : 1, 0, 0);
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_qkv);
       tma_prefetch_desc(&tm_do);
@@ -535,7 +537,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tma_prefetch_desc(&tm_dqkv);
       mbar_init(bar_ld, 1);
       mbar_init(bar_sdp, 1);
-      mbar_init(bar_pds, 128);
+      mbar_init(bar_pds, 256);
       mbar_init(bar_mma, 1);
       mbar_fence_init();
     }
@@ -548,7 +550,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t tmem = *tmem_holder;
   constexpr uint32_t cS = 0, cdP = 128, cdV = 256, cdK = 320, cdQ = 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(bar_ld, 5 * 32768);
 #pragma unroll
@@ -568,60 +570,64 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       constexpr uint32_t id_q = make_idesc_bf16(128, 64, false, true);   // dQ: A = dS (K-major), B = K (MN-major)
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), adO = smem_u32(sdO), aP = smem_u32(sP),
                      adS = smem_u32(sdS);
-      int it = 0;
-      for (int j = 0; j < 2; ++j) {
-        for (int i = 0; i < 2; ++i, ++it) {
+      // Issue order: S,dP(0) | for each block: wait P,dS(it) -> S,dP(it+1) -> dV,dK,dQ(it).  The score products of the next block go
+      // ahead of this block's gradient products, so the compute warps work on block it+1 (TMEM -> registers) while the tensor pipe
+      // is busy with dV,dK,dQ(it); they only wait for those (bar_mma) before overwriting the P / dS buffers.
+      auto issue_sdp = [&](int it) {
+        const int j = it >> 1, i = it & 1;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_ss(tmem + cS, make_sdesc_sw128(aQ + i * 16384 + k * 32, 16, 1024), make_sdesc_sw128(aK + j * 16384 + k * 32, 16, 1024),
-                      id_s, k > 0);
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(tmem + cS, make_sdesc_sw128(aQ + i * 16384 + k * 32, 16, 1024), make_sdesc_sw128(aK + j * 16384 + k * 32, 16, 1024),
+                    id_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_ss(tmem + cdP, make_sdesc_sw128(adO + i * 16384 + k * 32, 16, 1024), make_sdesc_sw128(aV + j * 16384 + k * 32, 16, 1024),
-                      id_s, k > 0);
-          tc_commit(bar_sdp);
-          DIG_STAMP(0, 1 + it, 0);
-          mbar_wait(bar_pds, it & 1);
-          tc_fence_after();
-          DIG_STAMP(0, 1 + it, 1);
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(tmem + cdP, make_sdesc_sw128(adO + i * 16384 + k * 32, 16, 1024), make_sdesc_sw128(aV + j * 16384 + k * 32, 16, 1024),
+                    id_s, k > 0);
+        tc_commit(bar_sdp);
+      };
+      issue_sdp(0);
+      DIG_STAMP(0, 1, 0);
+      for (int it = 0; it < 4; ++it) {
+        const int j = it >> 1, i = it & 1;
+        mbar_wait(bar_pds, it & 1);
+        tc_fence_after();
+        DIG_STAMP(0, 1 + it, 1);
+        if (it < 3) issue_sdp(it + 1);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
-            tc_mma_ss(tmem + cdV, make_sdesc_sw128(aP + k * 2048, 16384, 1024), make_sdesc_sw128(adO + i * 16384 + k * 2048, 8192, 1024),
-                      id_tt, (i > 0 || k > 0));
+        for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
+          tc_mma_ss(tmem + cdV, make_sdesc_sw128(aP + k * 2048, 16384, 1024), make_sdesc_sw128(adO + i * 16384 + k * 2048, 8192, 1024),
+                    id_tt, (i > 0 || k > 0));
 #pragma unroll
-          for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
-            tc_mma_ss(tmem + cdK, make_sdesc_sw128(adS + k * 2048, 16384, 1024), make_sdesc_sw128(aQ + i * 16384 + k * 2048, 8192, 1024),
-                      id_tt, (i > 0 || k > 0));
+        for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
+          tc_mma_ss(tmem + cdK, make_sdesc_sw128(adS + k * 2048, 16384, 1024), make_sdesc_sw128(aQ + i * 16384 + k * 2048, 8192, 1024),
+                    id_tt, (i > 0 || k > 0));
 #pragma unroll
-          for (int k = 0; k < 8; ++k)  // dQ_i += dS K_j     (reduction over 128 keys)
-            tc_mma_ss(tmem + cdQ + i * 64, make_sdesc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_sdesc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0));
-          tc_commit(bar_mma);
-          DIG_STAMP(0, 1 + it, 2);
-        }
+        for (int k = 0; k < 8; ++k)  // dQ_i += dS K_j     (reduction over 128 keys)
+          tc_mma_ss(tmem + cdQ + i * 64, make_sdesc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_sdesc_sw128(aK + j * 16384 + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0));
+        tc_commit(bar_mma);
+        DIG_STAMP(0, 1 + it, 2);
       }
     }
   } else {
-    const int t = threadIdx.x;  // row within a 128-token tile == TMEM lane
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const int t = (warp & 3) * 32 + lane;  // row within a 128-token tile == TMEM lane
+    const int hh = warp >> 2;              // which 64 key columns of a 128-key block (and which 32 head-dim columns of an output tile)
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float sl2 = scale * kLog2e;
     const uint32_t sP_s = smem_u32(sP), sdS_s = smem_u32(sdS), sdO_s = smem_u32(sdO);
-    // 128 x 64 fp32 accumulator rows (this thread's lane) -> bf16, times `mul`, into a swizzled staging tile for one TMA store
+    // this thread's 32 of the 64 columns of a 128-row fp32 accumulator -> bf16, times `mul`, into a swizzled staging tile (TMA store)
     auto stage_tile = [&](uint32_t tcol, uint32_t dst_s, float mul) {
+      uint32_t v[32];
+      tmem_ld32(tl + tcol + hh * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < kHd; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tl + tcol + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-          uint4 p;
-          p.x = pack_bf16(__uint_as_float(v[q + 0]) * mul, __uint_as_float(v[q + 1]) * mul);
-          p.y = pack_bf16(__uint_as_float(v[q + 2]) * mul, __uint_as_float(v[q + 3]) * mul);
-          p.z = pack_bf16(__uint_as_float(v[q + 4]) * mul, __uint_as_float(v[q + 5]) * mul);
-          p.w = pack_bf16(__uint_as_float(v[q + 6]) * mul, __uint_as_float(v[q + 7]) * mul);
-          sts_u4(dst_s + sw128_offset((uint32_t)t, (uint32_t)((c + q) >> 3)), p);
-        }
+      for (int q = 0; q < 32; q += 8) {
+        uint4 p;
+        p.x = pack_bf16(__uint_as_float(v[q + 0]) * mul, __uint_as_float(v[q + 1]) * mul);
+        p.y = pack_bf16(__uint_as_float(v[q + 2]) * mul, __uint_as_float(v[q + 3]) * mul);
+        p.z = pack_bf16(__uint_as_float(v[q + 4]) * mul, __uint_as_float(v[q + 5]) * mul);
+        p.w = pack_bf16(__uint_as_float(v[q + 6]) * mul, __uint_as_float(v[q + 7]) * mul);
+        sts_u4(dst_s + sw128_offset((uint32_t)t, (uint32_t)((hh * 32 + q) >> 3)), p);
       }
     };
     // D_i = rowsum(dO o O) from the TMA-staged tiles (a row-per-thread global read costs 32 LSU wavefronts per instruction), lse_i
@@ -641,78 +647,78 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
       Dr[i] = acc;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // every thread has read its O rows: the P buffer may be overwritten
-    int mma_seen = 0;
-    int it = 0;
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread has read its O rows: the P buffer may be overwritten
     DIG_STAMP(1, 0, 1);
-    for (int j = 0; j < 2; ++j) {
-      for (int i = 0; i < 2; ++i, ++it) {
-        DIG_STAMP(1, 1 + it, 0);
-        mbar_wait(bar_sdp, it & 1);
-        tc_fence_after();
-        DIG_STAMP(1, 1 + it, 1);
-        while (mma_seen < it) { mbar_wait(bar_mma, mma_seen & 1); ++mma_seen; }  // P/dS buffers free again
-        if (j == 1 && i == 0) {  // ... and so has the TMA store of dV_0 / dK_0 that was staged in them
-          if (t == 0) tma_store_wait_read_all();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        DIG_STAMP(1, 1 + it, 2);
-#pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
-          uint32_t s[32], g[32];
-          tmem_ld32(tl + cS + c, s);
-          tmem_ld32(tl + cdP + c, g);
-          tmem_ld_wait();
-          uint32_t pp[16], ds[16];
+    for (int it = 0; it < 4; ++it) {
+      const int j = it >> 1, i = it & 1;
+      DIG_STAMP(1, 1 + it, 0);
+      mbar_wait(bar_sdp, it & 1);
+      tc_fence_after();
+      DIG_STAMP(1, 1 + it, 1);
+      // phase A: S, dP (TMEM) -> P, dS as packed bf16 in registers; overlaps the tensor pipe's dV,dK,dQ of the previous block
+      uint32_t pp[32], ds[32];
 #pragma unroll
-          for (int q = 0; q < 32; q += 2) {
-            // dS is kept unscaled here; `scale` is applied once per output element when dK and dQ leave TMEM
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[q]), sl2, -Lr[i]));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[q + 1]), sl2, -Lr[i]));
-            const float d0 = p0 * (__uint_as_float(g[q]) - Dr[i]);
-            const float d1 = p1 * (__uint_as_float(g[q + 1]) - Dr[i]);
-            pp[q >> 1] = pack_bf16(p0, p1);
-            ds[q >> 1] = pack_bf16(d0, d1);
-          }
-          const uint32_t sub = (c >> 6) * 16384;
-          const uint32_t ch0 = (c & 63) >> 3;
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t s[32], g[32];
+        tmem_ld32(tl + cS + hh * 64 + c, s);
+        tmem_ld32(tl + cdP + hh * 64 + c, g);
+        tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const uint32_t off = sub + sw128_offset(t, ch0 + jj);
-            sts_u4(sP_s + off, make_uint4(pp[4 * jj], pp[4 * jj + 1], pp[4 * jj + 2], pp[4 * jj + 3]));
-            sts_u4(sdS_s + off, make_uint4(ds[4 * jj], ds[4 * jj + 1], ds[4 * jj + 2], ds[4 * jj + 3]));
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_pds);
-        DIG_STAMP(1, 1 + it, 3);
-        if (i == 1) {
-          while (mma_seen < it + 1) { mbar_wait(bar_mma, mma_seen & 1); ++mma_seen; }
-          tc_fence_after();
-          DIG_STAMP(1, 1 + it, 4);
-          // dV_j, dK_j: TMEM -> swizzled staging (the idle P / dS buffers) -> two TMA stores
-          stage_tile(cdV, sP_s, 1.0f);
-          stage_tile(cdK, sdS_s, scale);
-          tc_fence_before();
-          fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (t == 0) {
-            tma_store_2d(&tm_dqkv, sP_s, 2 * d + head * kHd, row0 + j * 128);
-            tma_store_2d(&tm_dqkv, sdS_s, d + head * kHd, row0 + j * 128);
-            tma_store_commit();
-          }
-          DIG_STAMP(1, 1 + it, 5);
+        for (int q = 0; q < 32; q += 2) {
+          // dS is kept unscaled here; `scale` is applied once per output element when dK and dQ leave TMEM
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[q]), sl2, -Lr[i]));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[q + 1]), sl2, -Lr[i]));
+          const float d0 = p0 * (__uint_as_float(g[q]) - Dr[i]);
+          const float d1 = p1 * (__uint_as_float(g[q + 1]) - Dr[i]);
+          pp[(c + q) >> 1] = pack_bf16(p0, p1);
+          ds[(c + q) >> 1] = pack_bf16(d0, d1);
         }
       }
+      // phase B: the previous block's products have read the P / dS buffers (and, for it == 2, so has the TMA store staged in them)
+      if (it > 0) {
+        mbar_wait(bar_mma, (it - 1) & 1);
+        tc_fence_after();
+      }
+      DIG_STAMP(1, 1 + it, 2);
+      if (it == 2) {
+        // dV_0, dK_0 are complete (bar_mma of block 1): TMEM -> the idle P / dS buffers -> two TMA stores
+        stage_tile(cdV, sP_s, 1.0f);
+        stage_tile(cdK, sdS_s, scale);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 0 && lane == 0) {
+          tma_store_2d(&tm_dqkv, sP_s, 2 * d + head * kHd, row0);
+          tma_store_2d(&tm_dqkv, sdS_s, d + head * kHd, row0);
+          tma_store_commit();
+          tma_store_wait_read_all();
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const uint32_t off = (uint32_t)hh * 16384u + sw128_offset((uint32_t)t, (uint32_t)jj);
+        sts_u4(sP_s + off, make_uint4(pp[4 * jj], pp[4 * jj + 1], pp[4 * jj + 2], pp[4 * jj + 3]));
+        sts_u4(sdS_s + off, make_uint4(ds[4 * jj], ds[4 * jj + 1], ds[4 * jj + 2], ds[4 * jj + 3]));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+      DIG_STAMP(1, 1 + it, 3);
     }
+    mbar_wait(bar_mma, 1);   // block 3: every accumulator is final
+    tc_fence_after();
     DIG_STAMP(1, 5, 0);
-    // dQ for both query tiles (complete after the last commit, which the i==1 wait above has seen); second halves of the staging buffers
+    // dV_1, dK_1 and dQ for both query tiles: the four 16 KB halves of the P / dS buffers stage one tile each
+    stage_tile(cdV, sP_s, 1.0f);
+    stage_tile(cdK, sdS_s, scale);
     stage_tile(cdQ, sP_s + 16384, scale);
     stage_tile(cdQ + 64, sdS_s + 16384, scale);
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (t == 0) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (warp == 0 && lane == 0) {
+      tma_store_2d(&tm_dqkv, sP_s, 2 * d + head * kHd, row0 + 128);
+      tma_store_2d(&tm_dqkv, sdS_s, d + head * kHd, row0 + 128);
       tma_store_2d(&tm_dqkv, sP_s + 16384, head * kHd, row0);
       tma_store_2d(&tm_dqkv, sdS_s + 16384, head * kHd, row0 + 128);
       tma_store_commit();
@@ -720,11 +726,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
   }
 
-  DIG_STAMP(warp == 4 ? 0 : 1, 5, 1);
+  DIG_STAMP(warp == 8 ? 0 : 1, 5, 1);
   tc_fence_before();
   __syncthreads();
-  DIG_STAMP(warp == 4 ? 0 : 1, 5, 2);
-  if (warp == 4) {
+  DIG_STAMP(warp == 8 ? 0 : 1, 5, 2);
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -795,7 +801,7 @@ extern "C" int dig_attention_bwd(const void* qkv, const void* out, const void* d
   const int smem = 196608 + 1024 + 128;
   static bool set = false;
   if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-  attn_bwd_kernel<<<(int)(num_seqs * heads), 160, smem, s>>>(tq, td, to, tg, lse, heads, scale);
+  attn_bwd_kernel<<<(int)(num_seqs * heads), kBwdThreads, smem, s>>>(tq, td, to, tg, lse, heads, scale);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
