@@ -260,13 +260,23 @@ def gpu_arm(a):
     for _ in range(2):
         step_resident()
     torch.cuda.synchronize()
-    flops, gms, n = ops.profile_gemm(False)
+    flops, gms, n, gbytes = ops.profile_gemm(False)
     sync_all()
     if rank == 0:
         peak, hbm, how = peaks()
         ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all encoder/head GEMM launches of the step)", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": how + " (sustained cuBLAS bf16)",
+        # DRAM traffic per launch of the same kernel family from the committed ncu pass (profiles/r1_step_metrics.json, written by
+        # scripts/ncu_step_metrics.sh + summarize_step_metrics.py on a B200); algorithmic bytes are counted live from the shapes.
+        traffic, tensor_pct, src = None, None, None
+        pj = os.path.join(ROOT, "profiles", "r1_step_metrics.json")
+        if os.path.isfile(pj) and a.batch == 128 and a.model == MODEL:
+            fam = json.load(open(pj)).get("gemm_family", {})
+            traffic, tensor_pct, src = fam.get("dram_bytes_per_launch"), fam.get("tensor_pipe_active_pct_time_weighted"), "profiles/r1_step_metrics.json"
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 / gemm2_bf16_tcgen05 (all encoder/head GEMM launches of the step)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": src, "algorithmic_bytes_per_launch": gbytes / max(n, 1),
+                "hbm_frac_at_algorithmic_bytes": (gbytes / (gms * 1e-3) / 1e9) / hbm if gms > 0 else None,
+                "ncu_tensor_pipe_active_pct": tensor_pct, "peak_source": how + " (sustained cuBLAS bf16)",
                 "launches_timed": n, "avg_launch_ms": gms / max(n, 1), "gemm_share_of_step": (gms / 2) / ms}
         gf = GFLOP_PER_CROP.get(a.model)
         if gf:

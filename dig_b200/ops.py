@@ -103,14 +103,15 @@ def count_launch(n=1):
 
 
 def profile_gemm(enable):
-    """Per-launch CUDA-event timing of dig_gemm.  profile_gemm(True) starts; profile_gemm(False) -> (flops, ms, launches)."""
+    """Per-launch CUDA-event timing of dig_gemm.  profile_gemm(True) starts; profile_gemm(False) -> (flops, ms, launches,
+    algorithmic HBM bytes: every operand and result of each launch counted once)."""
     global _gemm_prof
     if enable:
         _gemm_prof = []
         return None
     torch.cuda.synchronize()
     rec, _gemm_prof = _gemm_prof or [], None
-    return (sum(f for _, _, f in rec), sum(a.elapsed_time(b) for a, b, _ in rec), len(rec))
+    return (sum(r[2] for r in rec), sum(r[0].elapsed_time(r[1]) for r in rec), len(rec), sum(r[3] for r in rec))
 
 
 def call(name, *args):
@@ -194,7 +195,13 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
         e0.record()
         _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")
         e1.record()
-        _gemm_prof.append((e0, e1, 2.0 * M * N * K))
+        osz = out.element_size()
+        nbytes = 2.0 * (M * K + N * K) + M * N * osz * (split_k if split_k > 1 else 1)
+        if residual is not None:
+            nbytes += 4.0 * M * N
+        if aux is not None:
+            nbytes += 2.0 * M * N
+        _gemm_prof.append((e0, e1, 2.0 * M * N * K, nbytes))
     else:
         _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")
     count_launch()
