@@ -256,6 +256,8 @@ def gpu_arm(a):
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), timed per launch with CUDA events in a separate pass ----
     roof = None
+    if getattr(model, "_step", None) is not None:
+        model._step._two_streams = False   # per-launch GEMM timing: one stream, so no co-running kernel is inside a timed interval
     ops.profile_gemm(True)      # every rank runs the two extra steps (they contain collectives); rank 0 reports
     for _ in range(2):
         step_resident()

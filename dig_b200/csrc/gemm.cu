@@ -210,7 +210,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   if (TMA_EPI) {
     rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
     if (rc) return rc;
-    if (MODE == DIG_EPI_GELU || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
     else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
     if (rc) return rc;
   }
@@ -292,9 +292,11 @@ static bool use_2cta() {
 
 }  // namespace dig
 
-extern "C" int dig_gemm(const dig_gemm_t* g, void* stream) {
+extern "C" int dig_gemm(const dig_gemm_t* g_in, void* stream) {
   using namespace dig;
-  DIG_REQUIRE(g != nullptr, "dig_gemm: null descriptor");
+  DIG_REQUIRE(g_in != nullptr, "dig_gemm: null descriptor");
+  dig_gemm_t gg = *g_in;
+  const dig_gemm_t* g = &gg;
   DIG_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "dig_gemm: empty problem M=%lld N=%lld K=%lld", (long long)g->M, (long long)g->N,
               (long long)g->K);
   DIG_REQUIRE(g->A && g->B && g->out, "dig_gemm: null operand pointer");
@@ -304,16 +306,25 @@ extern "C" int dig_gemm(const dig_gemm_t* g, void* stream) {
               "dig_gemm: operands must be 16-byte aligned");
   DIG_REQUIRE(g->ldo % 4 == 0 && g->N % 4 == 0, "dig_gemm: N and ldo must be multiples of 4 (N=%lld ldo=%lld)", (long long)g->N, (long long)g->ldo);
   DIG_REQUIRE(!g->residual || g->ldr % 4 == 0, "dig_gemm: ldr must be a multiple of 4");
-  if (g->split_k > 1)
+  if (g->split_k > 1 || g->split_k < 0)
     DIG_REQUIRE(g->out_fp32 && g->epilogue == DIG_EPI_LINEAR && !g->bias && !g->residual && !g->row_mask && !g->colsum,
-                "dig_gemm: split_k>1 needs a plain fp32 accumulate epilogue");
-  if (g->epilogue != DIG_EPI_LINEAR) DIG_REQUIRE(g->aux != nullptr && g->ldaux % 4 == 0, "dig_gemm: epilogue %d needs aux", g->epilogue);
+                "dig_gemm: split_k needs a plain fp32 accumulate epilogue");
+  if (g->epilogue != DIG_EPI_LINEAR && !(g->epilogue == DIG_EPI_GELU && g->aux == nullptr))   // GELU forward: the pre-activation copy is optional
+    DIG_REQUIRE(g->aux != nullptr && g->ldaux % 4 == 0, "dig_gemm: epilogue %d needs aux", g->epilogue);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (use_2cta()) {
     const int r = gemm2_try(g, s);
     if (r <= 0) return r;
   }
   // tile width: 128 wherever N fills it, 64 for the narrow heads (pix_decoder 192/48)
-  if (g->N % 128 == 0 || g->N > 256) return dispatch<128>(g, s);
+  const int bn = (g->N % 128 == 0 || g->N > 256) ? 128 : 64;
+  if (g->split_k < 0) {  // auto split-K on the 1-CTA kernel: fill the SMs, at least 2 slices (the split epilogue accumulates into out)
+    const long long tiles = ((g->M + BM - 1) / BM) * ((g->N + bn - 1) / bn), num_kb = (g->K + BK - 1) / BK;
+    long long sp = num_sms() / (tiles > 0 ? tiles : 1);
+    if (sp < 2) sp = 2;
+    if (sp > num_kb) sp = num_kb;
+    gg.split_k = (int)sp;     // a single k-block problem degenerates to a plain store: out must then be zero-initialised (it is: gradients)
+  }
+  if (bn == 128) return dispatch<128>(g, s);
   return dispatch<64>(g, s);
 }

@@ -266,7 +266,7 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   if (TMA_EPI) {
     rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
     if (rc) return rc;
-    if (MODE == DIG_EPI_GELU || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
     else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
     if (rc) return rc;
   }
@@ -328,25 +328,44 @@ static int dispatch2(const dig_gemm_t* g, cudaStream_t s) {
   return 1;
 }
 
-int gemm2_try(const dig_gemm_t* g, cudaStream_t s) {
+int gemm2_try(const dig_gemm_t* g_in, cudaStream_t s) {
   // 2-CTA tiles are 256 rows tall: keep small problems (few tiles) on the 1-CTA kernel so they still spread over the SMs
+  dig_gemm_t gg = *g_in;
+  const dig_gemm_t* g = &gg;
   const long long m_tiles = (g->M + 255) / 256;
   const bool bmn = g->b_mn_major != 0;
+  const bool accumulate = g->split_k > 1 || g->split_k < 0;
+  static int wgrad_bn256 = -1, splitk_2cta = -1;
+  if (wgrad_bn256 < 0) { const char* e = getenv("DIG_GEMM_WGRAD_BN256"); wgrad_bn256 = e ? atoi(e) : 1; }
+  if (splitk_2cta < 0) { const char* e = getenv("DIG_GEMM_2CTA_SPLITK"); splitk_2cta = e ? atoi(e) : 1; }
+  if (accumulate && (!splitk_2cta || g->M * g->N <= 384 * 384)) return 1;   // small outputs: the 1-CTA kernel's 128-wide tiles waste less
   int bn;
   if (g->N % 256 == 0) bn = 256;
+  else if (accumulate && wgrad_bn256 && g->N > 256) bn = 256;   // split-K accumulate: ragged last tile, clipped by the tensor maps
   else if (g->N % 192 == 0 && !bmn) bn = 192;
   else if (g->N % 128 == 0) bn = 128;
   else return 1;
+  const long long tiles = m_tiles * ((g->N + bn - 1) / bn);
+  if (g->split_k < 0) {  // auto: as many K slices as fill the 74 CTA pairs (at least 2, so the epilogue accumulates)
+    const long long num_kb = (g->K + BK - 1) / BK;
+    long long sp = (num_sms() / 2) / (tiles > 0 ? tiles : 1);
+    if (sp < 2) sp = 2;
+    if (sp > num_kb) sp = num_kb;
+    if (sp < 2) return 1;
+    gg.split_k = (int)sp;
+  }
   const long long split = g->split_k > 1 ? g->split_k : 1;
-  if (m_tiles * ((g->N + bn - 1) / bn) * split < 32) return 1;
+  if (tiles * split < 32) return 1;
   // Measured on B200 (scripts/gemm_ab.py): with the TMA-staged epilogue the 2-CTA kernel wins or ties everywhere (erf-GELU forward:
-  // 110 us vs 130 us at 65536 x 1536 x 384 once the epilogue arithmetic is packed FFMA2) except split-K, where the 1-CTA kernel spreads
-  // the K slices over more CTAs.  DIG_GEMM_2CTA_MINK raises the K threshold, DIG_GEMM_2CTA_GELU=0 sends GELU back to 1-CTA (experiments).
+  // 110 us vs 130 us at 65536 x 1536 x 384 once the epilogue arithmetic is packed FFMA2).  Split-K accumulation runs on 256 x 256
+  // pair tiles as well: the 128 x 128 1-CTA tile is shared-memory-bandwidth bound (TMA fill + UMMA operand reads of 250 B/clk against
+  // 128 B/clk/SM), the pair tile needs half of that per FLOP.  DIG_GEMM_2CTA_MINK raises the K threshold, DIG_GEMM_2CTA_GELU=0 /
+  // DIG_GEMM_2CTA_SPLITK=0 / DIG_GEMM_WGRAD_BN256=0 switch the respective choices off (experiments).
   static int min_k = -1;
   if (min_k < 0) { const char* e = getenv("DIG_GEMM_2CTA_MINK"); min_k = e ? atoi(e) : 0; }
   static int gelu_2cta = -1;
   if (gelu_2cta < 0) { const char* e = getenv("DIG_GEMM_2CTA_GELU"); gelu_2cta = e ? atoi(e) : 1; }
-  if (g->K < min_k || split > 1 || (g->epilogue == DIG_EPI_GELU && !gelu_2cta)) return 1;
+  if (g->K < min_k || (g->epilogue == DIG_EPI_GELU && !gelu_2cta)) return 1;
   if (bn == 256) return dispatch2<256>(g, s);
   if (bn == 192) return dispatch2<192>(g, s);
   return dispatch2<128>(g, s);

@@ -101,7 +101,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const EpiPre<
       }
       f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
       if (MODE == DIG_EPI_GELU) {
-        st_bf16x4(reinterpret_cast<__nv_bfloat16*>(ep.aux) + grow * ep.ldaux + gcol, f);
+        if (ep.aux != nullptr) st_bf16x4(reinterpret_cast<__nv_bfloat16*>(ep.aux) + grow * ep.ldaux + gcol, f);
         f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w);
       } else if (MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_RELU_MASK) {
         const uint32_t lo = __float_as_uint(pre.v[i].x), hi = __float_as_uint(pre.v[i].y);

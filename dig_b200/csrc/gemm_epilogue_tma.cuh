@@ -147,7 +147,8 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
         }
         const uint32_t off = row_s + (((uint32_t)j ^ sw) << 4);
         if (MODE == DIG_EPI_GELU) {
-          sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+          if (ep.aux != nullptr)   // pre-activation copy for the backward; the no-grad momentum branch skips it (half the stores)
+            sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
 #if DIG_GELU_PACKED
 #pragma unroll
           for (int e = 0; e < 8; e += 2) gelu_erf_x2(f[e], f[e + 1], f[e], f[e + 1]);
@@ -197,7 +198,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
     if (lane == 0) {
       if (MODE == kEpiAtomic) tma_reduce_add_2d(tm_out, buf, gcol, row_base);
       else if (MODE == DIG_EPI_GELU) {
-        tma_store_2d(tm_aux, buf, gcol, row_base);   // pre-activation
+        if (ep.aux != nullptr) tma_store_2d(tm_aux, buf, gcol, row_base);   // pre-activation
         tma_store_2d(tm_out, buf2, gcol, row_base);  // gelu(pre)
       } else tma_store_2d(tm_out, buf, gcol, row_base);
       tma_store_commit();

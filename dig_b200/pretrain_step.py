@@ -69,12 +69,6 @@ class _Bufs:
         return t
 
 
-def _split_k(m, n, k, bn=128):
-    tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
-    kb = (k + 63) // 64
-    return max(1, min(kb, 148 // max(tiles, 1)))
-
-
 class PretrainStep:
     GEMM_WEIGHTS_BLOCK = ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")
 
@@ -102,6 +96,11 @@ class PretrainStep:
         self.saved = None
         self._n_masked = {}
         self._grad_flat = None
+        # The momentum branch (EMA update + no-grad forward) and the online branch are independent until the InfoNCE logits: they run
+        # on two streams so that one branch's HBM-bound kernels (LayerNorm, BatchNorm, casts) fill in under the other's GEMMs.
+        import os
+        self._two_streams = os.environ.get("DIG_TWO_STREAMS", "1") != "0"
+        self._side = torch.cuda.Stream(device=self.device) if self._two_streams else None
 
     # ------------------------------------------------------------------ parameter bookkeeping
     def _signature(self):
@@ -150,12 +149,13 @@ class PretrainStep:
         # fused qkv bias [q_bias | 0 | v_bias] per block (F:91) for both encoders
         d, L = self.d, self.depth
         self.qkv_bias = {"encoder.": torch.zeros(L, 3 * d, device=self.device), "momentum_encoder.": torch.zeros(L, 3 * d, device=self.device)}
-        src, dst = [], []
+        self.tab_qkv_bias = {}
         for pre in ("encoder.", "momentum_encoder."):
+            src, dst = [], []
             for l in range(L):
                 src += [self._named["%sblocks.%d.attn.q_bias" % (pre, l)].data, self._named["%sblocks.%d.attn.v_bias" % (pre, l)].data]
                 dst += [self.qkv_bias[pre][l, :d], self.qkv_bias[pre][l, 2 * d:]]
-        self.tab_qkv_bias = MtTable(self.device, src, dst)
+            self.tab_qkv_bias[pre] = MtTable(self.device, src, dst)
         # trainable parameters, in named_parameters order, and their flat gradient buffer
         self.train_names = [n for n, p in self._named.items() if p.requires_grad]
         goff, total = {}, 0
@@ -222,14 +222,14 @@ class PretrainStep:
             qkv = B.get(t + "qkv", (M, 3 * d), BF16)
             ops.gemm(ln1, bw["qkvw"], qkv, bias=bw["qkvb"])
             att = B.get(t + "att", (M, d), BF16)
-            lse = B.get(t + "lse", (S, h, TOK), F32)
+            lse = B.get(t + "lse", (S, h, TOK), F32) if save else None      # row log-sum-exp: only the backward reads it
             ops.attention_fwd(qkv, att, lse, h, self.scale)
             xm = B.get(t + "xm" if save else tag + "xm", (M, d), F32)
             ops.gemm(att, bw["pw"], xm, bias=bw["pb"], residual=x)
             ln2 = B.get(t + "ln2", (M, d), BF16)
             mean2, rstd2 = B.get(t + "m2", (M,), F32), B.get(t + "r2", (M,), F32)
             self._ln(xm, bw["n2w"], bw["n2b"], ln2, mean2, rstd2)
-            hpre = B.get(t + "hpre", (M, 4 * d), BF16)
+            hpre = B.get(t + "hpre", (M, 4 * d), BF16) if save else None     # GELU pre-activation: only the backward reads it
             hpost = B.get(t + "hpost", (M, 4 * d), BF16)
             ops.gemm(ln2, bw["f1w"], hpost, bias=bw["f1b"], epilogue=ops.EPI_GELU, aux=hpre)
             xn = B.get((tag + "x%d" % (l + 1)) if save else (tag + "x%d" % ((l + 1) % 2 + 1)), (M, d), F32)
@@ -257,21 +257,21 @@ class PretrainStep:
             bw, a = W["blocks"][l], sv["acts"][l]
             nm = bw["name"]
             # ---- MLP (F:53-60) ----
-            ops.gemm(gb, a["hpost"], grads[nm + "mlp.fc2.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(d, 4 * d, M))
+            ops.gemm(gb, a["hpost"], grads[nm + "mlp.fc2.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             ops.gemm(gb, bw["f2w"], dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=a["hpre"], colsum=grads[nm + "mlp.fc1.bias"])
-            ops.gemm(dh, a["ln2"], grads[nm + "mlp.fc1.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(4 * d, d, M))
+            ops.gemm(dh, a["ln2"], grads[nm + "mlp.fc1.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             ops.gemm(dh, bw["f1w"], dln, b_mn_major=True)
             call("dig_layernorm_bwd", dln, a["xm"], a["mean2"], a["rstd2"], bw["n2w"], None, g, g, gb,
                  grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], grads[nm + "attn.proj.bias"], M, d, 0)
             # ---- attention (F:87-125) ----
-            ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(d, d, M))
+            ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             ops.gemm(gb, bw["pw"], dat, b_mn_major=True)
             ops.attention_bwd(a["qkv"], a["att"], dat, a["lse"], dqkv, h, self.scale)
             dqkvb.zero_()
             call("dig_colsum", dqkv, 0, 3 * d, dqkvb, None, M, 3 * d)
             grads[nm + "attn.q_bias"].copy_(dqkvb[:d])
             grads[nm + "attn.v_bias"].copy_(dqkvb[2 * d:])
-            ops.gemm(dqkv, a["ln1"], grads[nm + "attn.qkv.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(3 * d, d, M))
+            ops.gemm(dqkv, a["ln1"], grads[nm + "attn.qkv.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             ops.gemm(dqkv, bw["qkvw"], dln, b_mn_major=True)
             prev_b2 = grads[W["blocks"][l - 1]["name"] + "mlp.fc2.bias"] if l > 0 else None
             call("dig_layernorm_bwd", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], None, g, g, gb,
@@ -286,7 +286,7 @@ class PretrainStep:
         call("dig_colsum", g, 1, d, tot, None, M, d)
         torch.sub(tot, grads[pre + "patch_embed.proj.bias"], out=grads[pre + "mask_token"].view(-1))
         ops.gemm(gz, sv["a0"], grads[pre + "patch_embed.proj.weight"].view(d, 48), a_mn_major=True, b_mn_major=True,
-                 split_k=_split_k(d, 48, M, 64))
+                 split_k=-1)
 
     # ------------------------------------------------------------------ BatchNorm MLP heads (M:463-482)
     def _mlp_layers(self, prefix, num_layers, seq):
@@ -339,7 +339,7 @@ class PretrainStep:
             call("dig_bn_bwd_apply", dy, sv["z"], sv["stats"], bst, sv["count"], bn.weight if bn.affine else None, bn.eps, dz, None, rows, C)
             a_in = sv["a_in"]
             Cin = a_in.shape[1]
-            ops.gemm(dz, a_in, grads[wname], a_mn_major=True, b_mn_major=True, split_k=_split_k(C, Cin, rows))
+            ops.gemm(dz, a_in, grads[wname], a_mn_major=True, b_mn_major=True, split_k=-1)
             if li > 0:
                 dy = B.get("%s.dy%d" % (tag, li), (rows, Cin), F32)
                 ops.gemm(dz, w, dy, b_mn_major=True, epilogue=ops.EPI_RELU_MASK, aux=a_in)
@@ -366,28 +366,32 @@ class PretrainStep:
         mask_u8.view(2, Bsz, TOK).copy_(vis_mask_pos.permute(1, 0, 2))      # M:496-497 view-major
 
         # bf16 shadows of the online weights + fused qkv bias
+        cur = torch.cuda.current_stream()
         self._mt("dig_mt_cast_bf16", self.tab_cast_online)
-        if not self.momentum_warm:
-            self._mt("dig_mt_cast_bf16", self.tab_cast_momentum)
-            self.momentum_warm = True
-        # ---- momentum branch first in stream order is fine: it only depends on the pre-step online weights ----
-        self._mt("dig_mt_ema", self.tab_ema, float(m))                       # M:526 (before the momentum forward)
-        self._mt("dig_mt_copy_f32", self.tab_qkv_bias)
-
-        Wm = self._enc_weights("momentum_encoder.")
-        enc_m, _ = self._encoder_fwd(Wm, images, mask_u8, "m.", save=False)
-        a0 = Bf.get("m.pp.in", (half, d), BF16)
-        call("dig_cast_f32_bf16", enc_m, a0, half * d)
-        ppm_layers = self._mlp_layers("pix_projector_m.", 3, model.pix_projector_m)
-        ppm_out, _, _ = self._mlp_fwd(a0, ppm_layers, "m.pp")
-        pooled_m = Bf.get("m.pooled", (S * self.num_windows, d), BF16)
-        call("dig_pool_fwd", ppm_out, enc_m[half:], Bsz, pooled_m, S, d, self.num_windows)
-        k, _, _ = self._mlp_fwd(pooled_m, self._mlp_layers("momentum_projection_layer.", 3, model.momentum_projection_layer), "m.proj")
-        R = k.shape[0]            # 2 * B * num_windows rows: [k1 ; k2]
-        Q, C = R // 2, k.shape[1]
-        kn = Bf.get("kn", (R, C), F32)
-        call("dig_l2norm_fwd", k, kn, None, R, C)
-        k1_all, k2_all = dist_layout.gather_keys(kn, Bf.get("kall", (world, R, C), F32) if world > 1 else None)  # M:580-591
+        self._mt("dig_mt_copy_f32", self.tab_qkv_bias["encoder."])
+        side = self._side if self._two_streams else cur
+        if side is not cur:
+            side.wait_stream(cur)       # staged inputs, and the optimizer step that produced the weights the EMA reads
+        with torch.cuda.stream(side):
+            if not self.momentum_warm:
+                self._mt("dig_mt_cast_bf16", self.tab_cast_momentum)
+                self.momentum_warm = True
+            self._mt("dig_mt_ema", self.tab_ema, float(m))                       # M:526 (before the momentum forward)
+            self._mt("dig_mt_copy_f32", self.tab_qkv_bias["momentum_encoder."])
+            Wm = self._enc_weights("momentum_encoder.")
+            enc_m, _ = self._encoder_fwd(Wm, images, mask_u8, "m.", save=False)
+            a0 = Bf.get("m.pp.in", (half, d), BF16)
+            call("dig_cast_f32_bf16", enc_m, a0, half * d)
+            ppm_layers = self._mlp_layers("pix_projector_m.", 3, model.pix_projector_m)
+            ppm_out, _, _ = self._mlp_fwd(a0, ppm_layers, "m.pp")
+            pooled_m = Bf.get("m.pooled", (S * self.num_windows, d), BF16)
+            call("dig_pool_fwd", ppm_out, enc_m[half:], Bsz, pooled_m, S, d, self.num_windows)
+            k, _, _ = self._mlp_fwd(pooled_m, self._mlp_layers("momentum_projection_layer.", 3, model.momentum_projection_layer), "m.proj")
+            R = k.shape[0]            # 2 * B * num_windows rows: [k1 ; k2]
+            Q, C = R // 2, k.shape[1]
+            kn = Bf.get("kn", (R, C), F32)
+            call("dig_l2norm_fwd", k, kn, None, R, C)
+            k1_all, k2_all = dist_layout.gather_keys(kn, Bf.get("kall", (world, R, C), F32) if world > 1 else None)  # M:580-591
 
         # ---- online branch ----
         W = self._enc_weights("encoder.")
@@ -407,6 +411,8 @@ class PretrainStep:
         call("dig_l2norm_fwd", q, qn, qinv, R, C)
 
         # ---- contrastive loss (M:444-461): q1.k2 + q2.k1 ----
+        if side is not cur:
+            cur.wait_stream(side)       # the keys (and the momentum weights the next EMA overwrites) are ready
         Nk = world * Q
         res = Bf.get("nce.res", (2, 4), F32)
         res.zero_()
@@ -506,17 +512,17 @@ class PretrainStep:
             dvf = d_vis.reshape(n_m, 48).to(F32).contiguous()
             call("dig_cast_f32_bf16", dvf, dv, n_m * 48)
             call("dig_colsum", dv, 0, 48, grads["pix_decoder.4.bias"], None, n_m, 48)
-            ops.gemm(dv, sv["t3"], grads["pix_decoder.4.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(48, 192, n_m, 64))
+            ops.gemm(dv, sv["t3"], grads["pix_decoder.4.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             dt3 = Bf.get("bw.dt3", (n_m, 192), BF16)
             ops.gemm(dv, S_["pix_decoder.4.weight"], dt3, b_mn_major=True)
             dt2 = Bf.get("bw.dt2", (n_m, 192), BF16)
             ln = model.pix_decoder[2]
             call("dig_layernorm_bwd", dt3, sv["t2"], sv["dmean"], sv["drstd"], ln.weight, ln.bias, None, None, dt2,
                  grads["pix_decoder.2.weight"], grads["pix_decoder.2.bias"], None, n_m, 192, 1)
-            ops.gemm(dt2, sv["t1"], grads["pix_decoder.1.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(192, 192, n_m, 64))
+            ops.gemm(dt2, sv["t1"], grads["pix_decoder.1.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             dt1 = Bf.get("bw.dt1", (n_m, 192), BF16)
             ops.gemm(dt2, S_["pix_decoder.1.weight"], dt1, b_mn_major=True)
-            ops.gemm(dt1, sv["g0"], grads["pix_decoder.0.weight"], a_mn_major=True, b_mn_major=True, split_k=_split_k(192, d, n_m, 64))
+            ops.gemm(dt1, sv["g0"], grads["pix_decoder.0.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             dg0 = Bf.get("bw.dg0", (n_m, d), F32)
             ops.gemm(dt1, S_["pix_decoder.0.weight"], dg0, b_mn_major=True)
             call("dig_scatter_add_rows", dg0, sv["idx"], g, n_m, d)

@@ -32,7 +32,7 @@ const char* dig_last_error(void); /* thread-local message of the last failing ca
  * B stored [K,N]); leading dimensions are in elements and must be multiples of 8.               */
 enum {
   DIG_EPI_LINEAR = 0,   /* v = alpha*acc (+bias[n]) (row-masked replace) (+residual)                       */
-  DIG_EPI_GELU = 1,     /* pre = alpha*acc + bias ; aux[m,n] (bf16) = pre ; v = gelu_erf(pre)   (F:54-55)   */
+  DIG_EPI_GELU = 1,     /* pre = alpha*acc + bias ; aux[m,n] (bf16) = pre if aux != NULL ; v = gelu_erf(pre) (F:54-55) */
   DIG_EPI_GELU_BWD = 2, /* v = alpha*acc * gelu_erf'(aux[m,n])  (aux: bf16 pre-activation)                 */
   DIG_EPI_RELU_MASK = 3 /* v = aux[m,n] > 0 ? alpha*acc : 0     (aux: bf16 post-ReLU activation)           */
 };
@@ -48,8 +48,10 @@ typedef struct dig_gemm {
   int32_t epilogue;
   void* aux; int64_t ldaux;
   float alpha;
-  int32_t split_k;                                 /* >1: K is split over CTAs, fp32 atomicAdd into out (out_fp32 must be 1,
-                                                      DIG_EPI_LINEAR without bias/residual); out must be pre-initialised */
+  int32_t split_k;                                 /* >1: K is split over CTAs, fp32 accumulate into out (out_fp32 must be 1,
+                                                      DIG_EPI_LINEAR without bias/residual); out must be pre-initialised.
+                                                      <0: same, the library picks the tile shape and the number of K slices
+                                                      that fill the SMs (weight gradients; out zero- or gradient-initialised) */
   float* colsum;                                   /* optional fp32 [N]: colsum[n] += sum_m out[m,n] (bias gradient of the layer
                                                       that produced the GEMM input), NULL to skip                        */
 } dig_gemm_t;

@@ -41,7 +41,7 @@ def wgrad(Mo, No):
     def mk():
         a, b = bf(M, Mo), bf(M, No)
         out = torch.zeros(Mo, No, device="cuda")
-        sk = int(os.environ.get("AB_SPLITK", 0)) or split_k(Mo, No, M)
+        sk = int(os.environ.get("AB_SPLITK", 0)) or -1
         return lambda: ops.gemm(a, b, out, a_mn_major=True, b_mn_major=True, split_k=sk)
     return mk
 fl = lambda n, k: 2.0 * M * n * k

@@ -48,6 +48,19 @@ def test_gemm_split_k_accumulates(ops):
     assert torch.allclose(out, ref, rtol=1e-4, atol=5e-2)
 
 
+@pytest.mark.parametrize("M,N", [(384, 1536), (1536, 384), (1152, 384), (384, 384), (48, 192), (192, 384)])
+def test_gemm_auto_split_k_weight_gradient_shapes(ops, M, N):
+    """split_k=-1: the library picks tile shape and K slices (2-CTA 256-wide pair tiles with ragged, clipped last tiles)."""
+    torch.manual_seed(7)
+    K = 4096 + 64
+    a, b = rnd(K, M, dtype=torch.bfloat16), rnd(K, N, dtype=torch.bfloat16)
+    base = rnd(M, N)
+    out = base.clone()
+    ops.gemm(a, b, out, a_mn_major=True, b_mn_major=True, split_k=-1)
+    ref = base + a.float().t() @ b.float()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=5e-2)
+
+
 def test_gemm_fused_epilogues(ops):
     torch.manual_seed(3)
     M, N, K = 640, 384, 384
