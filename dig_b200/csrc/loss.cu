@@ -34,53 +34,48 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 }
 
 // ---- fp32 GEMM on CUDA cores: C[M,N] = alpha * A[M,K] . (B_NT ? B[N,K]^T : B[K,N]) ----------------------
+// The InfoNCE logits (q.k^T / T, gain 5 on unit vectors) and their gradient stay in fp32; the problem is tiny (2 x 512 x 512W x 256 MAC),
+// so the tiles are small (32 x 32 outputs per CTA, 256 threads, 2 x 2 per thread) to put a few hundred CTAs on the 148 SMs, and every
+// global read is a 128-bit load along the contiguous dimension.  Requires K % 4 == 0 (and N % 4 == 0 for the [K,N] form).
 template <bool B_NT>
 __global__ void __launch_bounds__(256)
 sgemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, float alpha) {
-  __shared__ float sA[16][64 + 4];
-  __shared__ float sB[16][64 + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int kk = i & 15, mm = i >> 4;
-      const int gm = m0 + mm, gk = k0 + kk;
-      sA[kk][mm] = (gm < M && gk < K) ? A[(long long)gm * K + gk] : 0.f;
-    }
-    if (B_NT) {
-      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-        const int kk = i & 15, nn = i >> 4;
-        const int gn = n0 + nn, gk = k0 + kk;
-        sB[kk][nn] = (gn < N && gk < K) ? B[(long long)gn * K + gk] : 0.f;
-      }
-    } else {
-      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-        const int nn = i & 63, kk = i >> 6;
-        const int gn = n0 + nn, gk = k0 + kk;
-        sB[kk][nn] = (gn < N && gk < K) ? B[(long long)gk * N + gn] : 0.f;
+  __shared__ float sA[32][32 + 1];   // [k][m]
+  __shared__ float sB[32][32 + 1];   // [k][n]
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    {
+      const int r = t >> 3, c4 = (t & 7) * 4;   // 32 rows x 8 float4 along K
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M && k0 + c4 < K) v = *reinterpret_cast<const float4*>(A + (long long)(m0 + r) * K + k0 + c4);
+      sA[c4 + 0][r] = v.x; sA[c4 + 1][r] = v.y; sA[c4 + 2][r] = v.z; sA[c4 + 3][r] = v.w;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (B_NT) {
+        if (n0 + r < N && k0 + c4 < K) w = *reinterpret_cast<const float4*>(B + (long long)(n0 + r) * K + k0 + c4);
+        sB[c4 + 0][r] = w.x; sB[c4 + 1][r] = w.y; sB[c4 + 2][r] = w.z; sB[c4 + 3][r] = w.w;
+      } else {                                   // 32 k-rows x 8 float4 along N
+        if (k0 + r < K && n0 + c4 < N) w = *reinterpret_cast<const float4*>(B + (long long)(k0 + r) * N + n0 + c4);
+        sB[r][c4 + 0] = w.x; sB[r][c4 + 1] = w.y; sB[r][c4 + 2] = w.z; sB[r][c4 + 3] = w.w;
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    for (int kk = 0; kk < 32; ++kk) {
+      const float a0 = sA[kk][ty * 2], a1 = sA[kk][ty * 2 + 1], b0 = sB[kk][tx * 2], b1 = sB[kk][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
-      if (gm < M && gn < N) C[(long long)gm * N + gn] = acc[i][j] * alpha;
-    }
+  for (int i = 0; i < 2; ++i) {
+    const int gm = m0 + ty * 2 + i, gn = n0 + tx * 2;
+    if (gm < M && gn + 1 < N) *reinterpret_cast<float2*>(C + (long long)gm * N + gn) = make_float2(acc[i][0] * alpha, acc[i][1] * alpha);
+    else if (gm < M && gn < N) C[(long long)gm * N + gn] = acc[i][0] * alpha;
+  }
 }
 
 // ---- InfoNCE row pass: one block per query row over logits[Q, Nk] (already divided by T) ---------------
@@ -193,7 +188,10 @@ extern "C" int dig_l2norm_bwd(const float* dy, const float* y, const float* inv_
 extern "C" int dig_sgemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t b_is_nk, float alpha,
                              void* stream) {
   DIG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "dig_sgemm_f32: bad arguments");
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  DIG_REQUIRE(K % 4 == 0 && N % 2 == 0 && (b_is_nk || N % 4 == 0), "dig_sgemm_f32: K must be a multiple of 4 and N of %d (M=%d N=%d K=%d)",
+              b_is_nk ? 2 : 4, M, N, K);
+  DIG_REQUIRE((((uintptr_t)A | (uintptr_t)B) & 15) == 0 && ((uintptr_t)C & 7) == 0, "dig_sgemm_f32: operands must be 16-byte aligned");
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
   if (b_is_nk) sgemm_f32_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, alpha);
   else sgemm_f32_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, M, N, K, alpha);
   DIG_CHECK_CUDA(cudaGetLastError());

@@ -384,36 +384,47 @@ colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, fl
 // ------------------------------------------------------------------------------------------------
 // BatchNorm1d (training mode).  stats = [sum(C) | sumsq(C)] over `count` rows (possibly all-reduced across ranks).
 // ------------------------------------------------------------------------------------------------
+constexpr int kBnRows = 16;  // rows per thread in the BatchNorm elementwise kernels: per-column constants are computed once per 16 rows
+
 __global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, float count, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int relu, float eps, __nv_bfloat16* __restrict__ y_bf16,
                                 float* __restrict__ y_f32, long long rows, int C) {
+  // thread = 4 consecutive columns x kBnRows rows; consecutive threads take consecutive column groups (coalesced 16-byte accesses)
   const int cv = C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cv) return;
+  const long long chunks = (rows + kBnRows - 1) / kBnRows;
+  if (i >= chunks * cv) return;
   const int c = (int)(i % cv) * 4;
-  const long long r = i / cv;
-  const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
+  const long long r0 = (i / cv) * kBnRows;
   const float4 s = *reinterpret_cast<const float4*>(stats + c);
   const float4 q = *reinterpret_cast<const float4*>(stats + C + c);
   const float inv = 1.0f / count;
-  float o[4];
-  const float xv[4] = {v.x, v.y, v.z, v.w}, sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w};
+  const float sv[4] = {s.x, s.y, s.z, s.w}, qv[4] = {q.x, q.y, q.z, q.w};
+  float sc[4], sh[4];   // y = x * sc + sh
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float mu = sv[k] * inv;
-    const float var = fmaxf(qv[k] * inv - mu * mu, 0.f);
-    float t = (xv[k] - mu) * rsqrtf(var + eps);
-    if (gamma) t = t * gamma[c + k] + beta[c + k];
-    if (relu) t = fmaxf(t, 0.f);
-    o[k] = t;
+    const float rs = rsqrtf(fmaxf(qv[k] * inv - mu * mu, 0.f) + eps);
+    const float g = gamma ? gamma[c + k] : 1.f, bt = gamma ? beta[c + k] : 0.f;
+    sc[k] = rs * g;
+    sh[k] = bt - mu * rs * g;
   }
-  if (y_bf16) {
-    uint2 p;
-    p.x = pack_bf16(o[0], o[1]);
-    p.y = pack_bf16(o[2], o[3]);
-    *reinterpret_cast<uint2*>(y_bf16 + r * C + c) = p;
+  const long long r1 = r0 + kBnRows < rows ? r0 + kBnRows : rows;
+  for (long long r = r0; r < r1; ++r) {
+    const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
+    float o[4] = {fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3])};
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
+    }
+    if (y_bf16) {
+      uint2 p;
+      p.x = pack_bf16(o[0], o[1]);
+      p.y = pack_bf16(o[2], o[3]);
+      *reinterpret_cast<uint2*>(y_bf16 + r * C + c) = p;
+    }
+    if (y_f32) *reinterpret_cast<float4*>(y_f32 + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
-  if (y_f32) *reinterpret_cast<float4*>(y_f32 + r * C + c) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // running_mean/var update (momentum 0.1, unbiased variance), num_batches_tracked += 1
@@ -465,16 +476,39 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
                                     const float* __restrict__ bstats, float count, const float* __restrict__ gamma, float eps,
                                     __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dx_f32, long long rows, int C) {
+  // same decomposition as bn_apply_kernel; dx = a * dy + b * x + c0 with per-column a = gamma rstd, b = -a rstd^2 S2/n, c0 = -a S1/n - b mu
+  const int cv = C >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  const int c = (int)(i % C);
-  const float mu = stats[c] / count;
-  const float rs = rsqrtf(fmaxf(stats[C + c] / count - mu * mu, 0.f) + eps);
-  const float xh = (x[i] - mu) * rs;
-  const float g = gamma ? gamma[c] : 1.f;
-  const float v = g * rs * (dy[i] - bstats[c] / count - xh * bstats[C + c] / count);
-  if (dx_bf16) dx_bf16[i] = __float2bfloat16(v);
-  if (dx_f32) dx_f32[i] = v;
+  const long long chunks = (rows + kBnRows - 1) / kBnRows;
+  if (i >= chunks * cv) return;
+  const int c = (int)(i % cv) * 4;
+  const long long r0 = (i / cv) * kBnRows;
+  const float inv = 1.0f / count;
+  float ca[4], cb[4], cc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float mu = stats[c + k] * inv;
+    const float rs = rsqrtf(fmaxf(stats[C + c + k] * inv - mu * mu, 0.f) + eps);
+    const float g = gamma ? gamma[c + k] : 1.f;
+    const float m1 = bstats[c + k] * inv, m2 = bstats[C + c + k] * inv;   // mean(dy), mean(dy * xhat)
+    ca[k] = g * rs;
+    cb[k] = -ca[k] * rs * m2;             // xhat = (x - mu) rs
+    cc[k] = -ca[k] * m1 - cb[k] * mu;
+  }
+  const long long r1 = r0 + kBnRows < rows ? r0 + kBnRows : rows;
+  for (long long r = r0; r < r1; ++r) {
+    const float4 d4 = *reinterpret_cast<const float4*>(dy + r * C + c);
+    const float4 x4 = *reinterpret_cast<const float4*>(x + r * C + c);
+    const float o0 = fmaf(ca[0], d4.x, fmaf(cb[0], x4.x, cc[0])), o1 = fmaf(ca[1], d4.y, fmaf(cb[1], x4.y, cc[1]));
+    const float o2 = fmaf(ca[2], d4.z, fmaf(cb[2], x4.z, cc[2])), o3 = fmaf(ca[3], d4.w, fmaf(cb[3], x4.w, cc[3]));
+    if (dx_bf16) {
+      uint2 p;
+      p.x = pack_bf16(o0, o1);
+      p.y = pack_bf16(o2, o3);
+      *reinterpret_cast<uint2*>(dx_bf16 + r * C + c) = p;
+    }
+    if (dx_f32) *reinterpret_cast<float4*>(dx_f32 + r * C + c) = make_float4(o0, o1, o2, o3);
+  }
 }
 
 // fp32 -> bf16 elementwise
@@ -634,7 +668,7 @@ extern "C" int dig_bn_apply(const float* x, const float* stats, float count, con
                             void* y_bf16, float* y_f32, int64_t rows, int32_t C, void* stream) {
   DIG_REQUIRE(x && stats && rows > 0 && C % 4 == 0 && count > 0, "dig_bn_apply: bad arguments");
   DIG_REQUIRE((gamma == nullptr) == (beta == nullptr), "dig_bn_apply: gamma and beta must both be given or both be NULL");
-  bn_apply_kernel<<<blocks_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, stats, count, gamma, beta, relu, eps,
+  bn_apply_kernel<<<blocks_for(((rows + kBnRows - 1) / kBnRows) * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, stats, count, gamma, beta, relu, eps,
                                                                                    (__nv_bfloat16*)y_bf16, y_f32, rows, C);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -664,8 +698,8 @@ extern "C" int dig_bn_bwd_stats(const float* dy, const float* x, const float* st
 
 extern "C" int dig_bn_bwd_apply(const float* dy, const float* x, const float* stats, const float* bstats, float count, const float* gamma,
                                 float eps, void* dx_bf16, float* dx_f32, int64_t rows, int32_t C, void* stream) {
-  DIG_REQUIRE(dy && x && stats && bstats && rows > 0 && C > 0 && count > 0, "dig_bn_bwd_apply: bad arguments");
-  bn_bwd_apply_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, bstats, count, gamma, eps,
+  DIG_REQUIRE(dy && x && stats && bstats && rows > 0 && C > 0 && C % 4 == 0 && count > 0, "dig_bn_bwd_apply: bad arguments");
+  bn_bwd_apply_kernel<<<blocks_for(((rows + kBnRows - 1) / kBnRows) * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, bstats, count, gamma, eps,
                                                                                  (__nv_bfloat16*)dx_bf16, dx_f32, rows, C);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;

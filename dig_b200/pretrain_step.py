@@ -59,6 +59,7 @@ class _Bufs:
     def __init__(self, device):
         self.device = device
         self.d = {}
+        self.zero_lists = {}
 
     def get(self, name, shape, dtype):
         t = self.d.get(name)
@@ -66,7 +67,24 @@ class _Bufs:
         if t is None or tuple(t.shape) != shape or t.dtype != dtype:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self.d[name] = t
+            self.zero_lists = {k: [z for z in v if z[0] != name] for k, v in self.zero_lists.items()}
         return t
+
+    def zeroed(self, name, shape, dtype, phase):
+        """A small accumulator buffer that must be zero when its consumer runs.  The first time it is zeroed on the spot; from then on
+        `zero_phase(phase)` clears every accumulator of the phase ("fwd" / "bwd") with ONE multi-tensor launch at the start of the
+        phase instead of one memset per layer (41 launches per step before)."""
+        t = self.get(name, shape, dtype)
+        lst = self.zero_lists.setdefault(phase, [])
+        if not any(z[0] == name for z in lst):
+            t.zero_()
+            lst.append((name, t))
+        return t
+
+    def zero_phase(self, phase):
+        lst = self.zero_lists.get(phase)
+        if lst:
+            torch._foreach_zero_([t for _, t in lst])
 
 
 class PretrainStep:
@@ -249,7 +267,6 @@ class PretrainStep:
         dln = B.get("bw.dln", (M, d), BF16)
         dat = B.get("bw.dat", (M, d), BF16)
         dqkv = B.get("bw.dqkv", (M, 3 * d), BF16)
-        dqkvb = B.get("bw.dqkvb", (3 * d,), F32)
         # fc2 bias gradient of the last block = column sums of the incoming gradient; for the other blocks it falls out of
         # the LayerNorm-1 backward of the block above (dxsum), like the proj bias gradient out of the LayerNorm-2 backward.
         call("dig_colsum", gb, 0, d, grads[W["blocks"][-1]["name"] + "mlp.fc2.bias"], None, M, d)
@@ -267,7 +284,7 @@ class PretrainStep:
             ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             ops.gemm(gb, bw["pw"], dat, b_mn_major=True)
             ops.attention_bwd(a["qkv"], a["att"], dat, a["lse"], dqkv, h, self.scale)
-            dqkvb.zero_()
+            dqkvb = B.zeroed("bw.dqkvb%d" % l, (3 * d,), F32, "bwd")
             call("dig_colsum", dqkv, 0, 3 * d, dqkvb, None, M, 3 * d)
             grads[nm + "attn.q_bias"].copy_(dqkvb[:d])
             grads[nm + "attn.v_bias"].copy_(dqkvb[2 * d:])
@@ -281,8 +298,7 @@ class PretrainStep:
         gz = B.get("bw.gz", (M, d), BF16)
         call("dig_zero_masked_rows", g, sv["mask"], gz, M, d)
         call("dig_colsum", gz, 0, d, grads[pre + "patch_embed.proj.bias"], None, M, d)
-        tot = B.get("bw.tot", (d,), F32)
-        tot.zero_()
+        tot = B.zeroed("bw.tot", (d,), F32, "bwd")
         call("dig_colsum", g, 1, d, tot, None, M, d)
         torch.sub(tot, grads[pre + "patch_embed.proj.bias"], out=grads[pre + "mask_token"].view(-1))
         ops.gemm(gz, sv["a0"], grads[pre + "patch_embed.proj.weight"].view(d, 48), a_mn_major=True, b_mn_major=True,
@@ -304,8 +320,7 @@ class PretrainStep:
             C = w.shape[0]
             z = B.get("%s.z%d" % (tag, li), (rows, C), F32)
             ops.gemm(a, w, z)
-            stats = B.get("%s.st%d" % (tag, li), (2 * C,), F32)
-            stats.zero_()
+            stats = B.zeroed("%s.st%d" % (tag, li), (2 * C,), F32, "fwd")
             call("dig_colsum", z, 1, C, stats, stats[C:], rows, C)
             count = dist_layout.sync_batch_stats(stats, rows) if self._bn_sync(bn) else float(rows)
             a_out = B.get("%s.a%d" % (tag, li), (rows, C), BF16) if (not last or want_bf16_out) else None
@@ -327,8 +342,7 @@ class PretrainStep:
             w, bn, wname, bnname = layers[li]
             sv = saved[li]
             C = w.shape[0]
-            bst = B.get("%s.bst%d" % (tag, li), (2 * C,), F32)
-            bst.zero_()
+            bst = B.zeroed("%s.bst%d" % (tag, li), (2 * C,), F32, "bwd")
             call("dig_bn_bwd_stats", dy, sv["z"], sv["stats"], sv["count"], bn.eps, bst, rows, C)
             if bn.affine:
                 grads[bnname + "bias"].copy_(bst[:C])
@@ -365,6 +379,7 @@ class PretrainStep:
         mask_u8 = Bf.get("mask", (M,), torch.uint8)
         mask_u8.view(2, Bsz, TOK).copy_(vis_mask_pos.permute(1, 0, 2))      # M:496-497 view-major
 
+        Bf.zero_phase("fwd")
         # bf16 shadows of the online weights + fused qkv bias
         cur = torch.cuda.current_stream()
         self._mt("dig_mt_cast_bf16", self.tab_cast_online)
@@ -414,8 +429,7 @@ class PretrainStep:
         if side is not cur:
             cur.wait_stream(side)       # the keys (and the momentum weights the next EMA overwrites) are ready
         Nk = world * Q
-        res = Bf.get("nce.res", (2, 4), F32)
-        res.zero_()
+        res = Bf.zeroed("nce.res", (2, 4), F32, "fwd")
         lg1 = Bf.get("nce.lg1", (Q, Nk), F32)
         lg2 = Bf.get("nce.lg2", (Q, Nk), F32)
         call("dig_sgemm_f32", qn[:Q], k2_all, lg1, Q, Nk, C, 1, 1.0 / self.T)
@@ -427,8 +441,7 @@ class PretrainStep:
         n_per = self._masked_per_sample(vis_mask_pos)
         n_m = Bsz * n_per
         idx = Bf.get("dec.idx", (max(n_m, 1),), torch.int32)
-        err = Bf.get("dec.err", (1,), torch.int32)
-        err.zero_()
+        err = Bf.zeroed("dec.err", (1,), torch.int32, "fwd")
         call("dig_mask_to_index", mask_u8, idx, err, Bsz, n_per)
         g0 = Bf.get("dec.g0", (n_m, d), BF16)
         call("dig_gather_rows", enc, idx, g0, n_m, d)
@@ -482,6 +495,7 @@ class PretrainStep:
             flat = self._grad_flat
             flat.zero_()
         grads = self._grad_views(flat)
+        Bf.zero_phase("bwd")
         g = Bf.get("bw.g", (M, d), F32)
         S_ = self.shadow
 
