@@ -736,6 +736,254 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, persistent: one CTA per SM walks (sequence, head) items.  Same block schedule as attn_bwd_kernel (4 blocks of 128 queries x
+// 128 keys per item, P/dS held in registers across the previous block's gradient products), plus:
+//   * D = rowsum(dO o O) comes in precomputed (the output-projection dgrad GEMM emits it, DIG_EPI_ROWDOT), so O is never read here;
+//   * operand tiles live in rings -- three (Q_i | dO_i) slots and two (K_j | V_j) slots -- that a dedicated TMA warp refills as soon as
+//     the MMA thread's commits release them: the next item's first tiles land while this item is still computing, which hides the
+//     ~5 us load latency that the one-shot kernel pays per item (1 CTA per SM: nobody else covers it);
+//   * the last outputs of item n (dV_1, dK_1, dQ_0, dQ_1) are staged and stored while the tensor pipe already works on item n+1.
+// Warps 0-7 compute (warp & 3 = TMEM lane quarter, warp >> 2 = which 64 key columns / 32 output columns), warp 8 = MMA issue + TMEM
+// owner, warp 9 = TMA producer.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kBwdPThreads = 320;
+static constexpr uint32_t kBwdQdO = 0, kBwdKV = 98304, kBwdP = 163840, kBwdDS = 196608, kBwdBars = 229376;
+
+__global__ void __launch_bounds__(kBwdPThreads, 1)
+attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse, const float* __restrict__ Dsum, int heads,
+                        float scale, int num_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdBars);
+  uint64_t* qdo_full = bars + 0;    // [3]
+  uint64_t* qdo_empty = bars + 3;   // [3]
+  uint64_t* kv_full = bars + 6;     // [2]
+  uint64_t* kv_empty = bars + 8;    // [2]
+  uint64_t* bar_sdp = bars + 10;
+  uint64_t* bar_pds = bars + 11;
+  uint64_t* bar_mma = bars + 12;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * kHd;
+  const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_items * 4;   // blocks (it = 2 j + i) this CTA processes
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqkv);
+    for (int i = 0; i < 3; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(bar_sdp, 1);
+    mbar_init(bar_pds, 256);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_holder, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  constexpr uint32_t cS = 0, cdP = 128, cdV = 256, cdK = 320, cdQ = 384;
+
+  if (warp == 9) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int n = 0;
+      for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++n) {
+        const int head = w % heads, row0 = (w / heads) * kTok;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int T = 2 * n + i, sl = T % 3;
+          const uint32_t use = (uint32_t)(T / 3) & 1u;
+          uint8_t* q = smem + kBwdQdO + sl * 32768;
+          mbar_wait(&qdo_empty[sl], use ^ 1u);
+          mbar_expect_tx(&qdo_full[sl], 32768);
+          tma_load_2d(q, &tm_qkv, &qdo_full[sl], head * kHd, row0 + i * 128);
+          tma_load_2d(q + 16384, &tm_do, &qdo_full[sl], head * kHd, row0 + i * 128);
+          uint8_t* kv = smem + kBwdKV + i * 32768;   // K_j | V_j with j = i
+          mbar_wait(&kv_empty[i], ((uint32_t)n & 1u) ^ 1u);
+          mbar_expect_tx(&kv_full[i], 32768);
+          tma_load_2d(kv, &tm_qkv, &kv_full[i], d + head * kHd, row0 + i * 128);
+          tma_load_2d(kv + 16384, &tm_qkv, &kv_full[i], 2 * d + head * kHd, row0 + i * 128);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && total > 0) {
+      constexpr uint32_t id_s = make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t id_tt = make_idesc_bf16(128, 64, true, true);   // dV, dK: A = P^T / dS^T (MN-major), B MN-major
+      constexpr uint32_t id_q = make_idesc_bf16(128, 64, false, true);   // dQ: A = dS (K-major), B = K (MN-major)
+      const uint32_t base = smem_u32(smem), aP = base + kBwdP, adS = base + kBwdDS;
+      auto qdo_slot = [&](int g) { return (2 * (g >> 2) + (g & 1)) % 3; };                       // ring slot of (Q_i | dO_i) for block g
+      auto issue_sdp = [&](int g) {   // S = Q_i K_j^T, dP = dO_i V_j^T for block g (waits for its tiles)
+        const int n = g >> 2, j = (g >> 1) & 1, T = 2 * n + (g & 1), sl = T % 3;
+        mbar_wait(&qdo_full[sl], (uint32_t)(T / 3) & 1u);
+        mbar_wait(&kv_full[j], (uint32_t)n & 1u);
+        tc_fence_after();
+        const uint32_t aQ = base + kBwdQdO + sl * 32768, adO = aQ + 16384, aK = base + kBwdKV + j * 32768, aV = aK + 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(tmem + cS, make_sdesc_sw128(aQ + k * 32, 16, 1024), make_sdesc_sw128(aK + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_ss(tmem + cdP, make_sdesc_sw128(adO + k * 32, 16, 1024), make_sdesc_sw128(aV + k * 32, 16, 1024), id_s, k > 0);
+        tc_commit(bar_sdp);
+      };
+      issue_sdp(0);
+      for (int g = 0; g < total; ++g) {
+        const int it = g & 3, j = it >> 1, i = it & 1, sl = qdo_slot(g);
+        const uint32_t aQ = base + kBwdQdO + sl * 32768, adO = aQ + 16384, aK = base + kBwdKV + j * 32768;
+        mbar_wait(bar_pds, (uint32_t)g & 1u);
+        tc_fence_after();
+        if (g + 1 < total) issue_sdp(g + 1);   // the next block's scores go ahead of this block's gradient products
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
+          tc_mma_ss(tmem + cdV, make_sdesc_sw128(aP + k * 2048, 16384, 1024), make_sdesc_sw128(adO + k * 2048, 8192, 1024), id_tt,
+                    (i > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
+          tc_mma_ss(tmem + cdK, make_sdesc_sw128(adS + k * 2048, 16384, 1024), make_sdesc_sw128(aQ + k * 2048, 8192, 1024), id_tt,
+                    (i > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ_i += dS K_j     (reduction over 128 keys)
+          tc_mma_ss(tmem + cdQ + i * 64, make_sdesc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_sdesc_sw128(aK + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0));
+        tc_commit(bar_mma);
+        // ring releases: a commit arrives once every MMA issued so far (including the S,dP of block g+1 above) has completed
+        if (it == 1) tc_commit(&kv_empty[0]);
+        else if (it == 2) tc_commit(&qdo_empty[qdo_slot(g)]);             // (Q_0 | dO_0): blocks 0 and 2
+        else if (it == 3) { tc_commit(&qdo_empty[sl]); tc_commit(&kv_empty[1]); }
+      }
+    }
+  } else {
+    // ===================== compute warps =====================
+    const int t = (warp & 3) * 32 + lane;  // row within a 128-token tile == TMEM lane
+    const int hh = warp >> 2;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sl2 = scale * kLog2e;
+    const uint32_t sP_s = smem_u32(smem) + kBwdP, sdS_s = smem_u32(smem) + kBwdDS;
+    const bool storer = (warp == 0 && lane == 0);
+    auto stage_tile = [&](uint32_t tcol, uint32_t dst_s, float mul) {
+      uint32_t v[32];
+      tmem_ld32(tl + tcol + hh * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; q += 8) {
+        uint4 p;
+        p.x = pack_bf16(__uint_as_float(v[q + 0]) * mul, __uint_as_float(v[q + 1]) * mul);
+        p.y = pack_bf16(__uint_as_float(v[q + 2]) * mul, __uint_as_float(v[q + 3]) * mul);
+        p.z = pack_bf16(__uint_as_float(v[q + 4]) * mul, __uint_as_float(v[q + 5]) * mul);
+        p.w = pack_bf16(__uint_as_float(v[q + 6]) * mul, __uint_as_float(v[q + 7]) * mul);
+        sts_u4(dst_s + sw128_offset((uint32_t)t, (uint32_t)((hh * 32 + q) >> 3)), p);
+      }
+    };
+    // dV_1, dK_1, dQ_0, dQ_1 of the item (head, row0): the four 16 KB halves of the P / dS buffers stage one tile each
+    auto store_item_tail = [&](int head, int row0) {
+      stage_tile(cdV, sP_s, 1.0f);
+      stage_tile(cdK, sdS_s, scale);
+      stage_tile(cdQ, sP_s + 16384, scale);
+      stage_tile(cdQ + 64, sdS_s + 16384, scale);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (storer) {
+        tma_store_2d(&tm_dqkv, sP_s, 2 * d + head * kHd, row0 + 128);
+        tma_store_2d(&tm_dqkv, sdS_s, d + head * kHd, row0 + 128);
+        tma_store_2d(&tm_dqkv, sP_s + 16384, head * kHd, row0);
+        tma_store_2d(&tm_dqkv, sdS_s + 16384, head * kHd, row0 + 128);
+        tma_store_commit();
+      }
+    };
+    float Dr[2] = {0.f, 0.f}, Lr[2] = {0.f, 0.f};
+    int head = 0, row0 = 0, prev_head = 0, prev_row0 = 0;
+    for (int g = 0; g < total; ++g) {
+      const int it = g & 3, i = it & 1;
+      if (it == 0) {
+        prev_head = head; prev_row0 = row0;
+        const int w = (int)blockIdx.x + (g >> 2) * (int)gridDim.x;
+        head = w % heads; row0 = (w / heads) * kTok;
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          Lr[ii] = lse[((long long)(row0 / kTok) * heads + head) * kTok + ii * 128 + t] * kLog2e;
+          Dr[ii] = Dsum[(long long)(row0 + ii * 128 + t) * heads + head];
+        }
+      }
+      mbar_wait(bar_sdp, (uint32_t)g & 1u);
+      tc_fence_after();
+      // phase A: S, dP (TMEM) -> P, dS as packed bf16 in registers; overlaps the tensor pipe's dV,dK,dQ of the previous block
+      uint32_t pp[32], ds[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t sv[32], gv[32];
+        tmem_ld32(tl + cS + hh * 64 + c, sv);
+        tmem_ld32(tl + cdP + hh * 64 + c, gv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[q]), sl2, -Lr[i]));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[q + 1]), sl2, -Lr[i]));
+          const float d0 = p0 * (__uint_as_float(gv[q]) - Dr[i]);
+          const float d1 = p1 * (__uint_as_float(gv[q + 1]) - Dr[i]);
+          pp[(c + q) >> 1] = pack_bf16(p0, p1);
+          ds[(c + q) >> 1] = pack_bf16(d0, d1);
+        }
+      }
+      // phase B: the previous block's gradient products have read the P / dS buffers
+      if (g > 0) {
+        mbar_wait(bar_mma, (uint32_t)(g - 1) & 1u);
+        tc_fence_after();
+      }
+      if (it == 2) {
+        // dV_0, dK_0 are final (block 1): TMEM -> the idle P / dS buffers -> two TMA stores
+        stage_tile(cdV, sP_s, 1.0f);
+        stage_tile(cdK, sdS_s, scale);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (storer) {
+          tma_store_2d(&tm_dqkv, sP_s, 2 * d + head * kHd, row0);
+          tma_store_2d(&tm_dqkv, sdS_s, d + head * kHd, row0);
+          tma_store_commit();
+          tma_store_wait_read_all();
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else if (it == 0 && g > 0) {
+        // the previous item is complete (its block 3): drain its last four tiles, then reuse the buffers for this item's block 0
+        store_item_tail(prev_head, prev_row0);
+        if (storer) tma_store_wait_read_all();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const uint32_t off = (uint32_t)hh * 16384u + sw128_offset((uint32_t)t, (uint32_t)jj);
+        sts_u4(sP_s + off, make_uint4(pp[4 * jj], pp[4 * jj + 1], pp[4 * jj + 2], pp[4 * jj + 3]));
+        sts_u4(sdS_s + off, make_uint4(ds[4 * jj], ds[4 * jj + 1], ds[4 * jj + 2], ds[4 * jj + 3]));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_pds);
+    }
+    if (total > 0) {
+      mbar_wait(bar_mma, (uint32_t)(total - 1) & 1u);
+      tc_fence_after();
+      store_item_tail(head, row0);
+      if (storer) tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace dig
 
 // bring-up only (not part of include/dig_b200.h): device buffer of 3 x 12 x 8 int64 clock stamps, or NULL to switch recording off
@@ -802,6 +1050,32 @@ extern "C" int dig_attention_bwd(const void* qkv, const void* out, const void* d
   static bool set = false;
   if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
   attn_bwd_kernel<<<(int)(num_seqs * heads), kBwdThreads, smem, s>>>(tq, td, to, tg, lse, heads, scale);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Persistent backward: D = rowsum(dO o O) [num_seqs*256, heads] fp32 is supplied by the caller (dig_gemm with DIG_EPI_ROWDOT on the
+// output-projection dgrad), so the forward output is not read.
+extern "C" int dig_attention_bwd_d(const void* qkv, const void* dout, const float* lse, const float* dsum, void* dqkv, int64_t num_seqs,
+                                   int32_t heads, float scale, void* stream) {
+  using namespace dig;
+  DIG_REQUIRE(qkv && dout && lse && dsum && dqkv, "dig_attention_bwd_d: null pointer");
+  DIG_REQUIRE(num_seqs > 0 && heads > 0, "dig_attention_bwd_d: empty problem");
+  const int d = heads * kHd;
+  CUtensorMap tq, td, tg;
+  int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)num_seqs * kTok, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&td, dout, (uint64_t)num_seqs * kTok, (uint64_t)d, (uint64_t)d, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tg, dqkv, (uint64_t)num_seqs * kTok, (uint64_t)3 * d, (uint64_t)3 * d, 128, 64);
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int smem = (int)kBwdBars + 256 + 1024;
+  static bool set = false;
+  if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  const int items = (int)(num_seqs * heads);
+  const int ctas = items < num_sms() ? items : num_sms();
+  attn_bwd_persist_kernel<<<ctas, kBwdPThreads, smem, s>>>(tq, td, tg, lse, dsum, heads, scale, items);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -210,7 +210,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   if (TMA_EPI) {
     rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
     if (rc) return rc;
-    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_ROWDOT) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
     else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
     if (rc) return rc;
   }
@@ -227,6 +227,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
   ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.colsum = g->colsum;
+  ep.rowdot = g->rowdot; ep.ldrowdot = g->ldrowdot; ep.M = (int)g->M;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
   if (g->colsum) DIG_REQUIRE(g->epilogue == DIG_EPI_GELU_BWD && g->N <= 2048, "dig_gemm: colsum is built for DIG_EPI_GELU_BWD with N <= 2048 only");
 
@@ -263,6 +264,7 @@ static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
   DIG_CASE_T(false, true, DIG_EPI_LINEAR, false)    // dgrad -> bf16
   DIG_CASE_T(false, true, DIG_EPI_LINEAR, true)     // dgrad -> fp32
   DIG_CASE_T(false, true, DIG_EPI_GELU_BWD, false)  // fc2 dgrad * gelu'
+  if (tma_ok) { DIG_CASE_T(false, true, DIG_EPI_ROWDOT, false) }   // proj dgrad + D = rowsum(dO o O) per head (TMA epilogue only)
   DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)  // BN-MLP dgrad through ReLU
   DIG_CASE_T(true, true, DIG_EPI_LINEAR, true)      // wgrad, single pass
   DIG_CASE_T(true, true, kEpiAtomic, true)          // wgrad, split-K
@@ -309,6 +311,9 @@ extern "C" int dig_gemm(const dig_gemm_t* g_in, void* stream) {
   if (g->split_k > 1 || g->split_k < 0)
     DIG_REQUIRE(g->out_fp32 && g->epilogue == DIG_EPI_LINEAR && !g->bias && !g->residual && !g->row_mask && !g->colsum,
                 "dig_gemm: split_k needs a plain fp32 accumulate epilogue");
+  if (g->epilogue == DIG_EPI_ROWDOT)
+    DIG_REQUIRE(g->rowdot != nullptr && g->ldrowdot * 64 >= g->N && g->N % 64 == 0 && !g->out_fp32 && g->split_k == 1,
+                "dig_gemm: DIG_EPI_ROWDOT needs bf16 out, N %% 64 == 0 and rowdot[M, >= N/64]");
   if (g->epilogue != DIG_EPI_LINEAR && !(g->epilogue == DIG_EPI_GELU && g->aux == nullptr))   // GELU forward: the pre-activation copy is optional
     DIG_REQUIRE(g->aux != nullptr && g->ldaux % 4 == 0, "dig_gemm: epilogue %d needs aux", g->epilogue);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -266,7 +266,7 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   if (TMA_EPI) {
     rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
     if (rc) return rc;
-    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_ROWDOT) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
     else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
     if (rc) return rc;
   }
@@ -283,6 +283,7 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
   ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.colsum = g->colsum;
+  ep.rowdot = g->rowdot; ep.ldrowdot = g->ldrowdot; ep.M = (int)g->M;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
 
   auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32, TMA_EPI>;
@@ -319,6 +320,7 @@ static int dispatch2(const dig_gemm_t* g, cudaStream_t s) {
     DIG_CASE_T(false, true, DIG_EPI_LINEAR, false)
     DIG_CASE_T(false, true, DIG_EPI_LINEAR, true)
     DIG_CASE_T(false, true, DIG_EPI_GELU_BWD, false)
+    if (tma_ok) { DIG_CASE_T(false, true, DIG_EPI_ROWDOT, false) }
     DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)
     DIG_CASE_T(true, true, DIG_EPI_LINEAR, true)
     DIG_CASE_T(true, true, kEpiAtomic, true)

@@ -28,6 +28,9 @@ struct GemmEpilogue {
   long long ldaux;
   float alpha;
   float* colsum;
+  float* rowdot;      // DIG_EPI_ROWDOT (TMA epilogue only)
+  long long ldrowdot;
+  int M;
   int dbg;  // bring-up only (env DIG_GEMM_DBG): 1 = skip the global stores, 2 = skip the whole epilogue body
 };
 

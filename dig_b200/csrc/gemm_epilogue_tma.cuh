@@ -44,7 +44,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
   constexpr int G = OUT_F32 ? 32 : 64;            // columns per 128-byte staging row
   constexpr int NGT = (BNT + G - 1) / G;          // column groups in the tile
   static_assert(BNT % G == 0, "tile width must be a multiple of the staging group");
-  const bool has_ld = (MODE == DIG_EPI_GELU_BWD) || (MODE == DIG_EPI_LINEAR && OUT_F32 && ep.residual != nullptr);
+  const bool has_ld = (MODE == DIG_EPI_GELU_BWD) || (MODE == DIG_EPI_ROWDOT) || (MODE == DIG_EPI_LINEAR && OUT_F32 && ep.residual != nullptr);
   const uint32_t row_s = (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7);
 
@@ -128,6 +128,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
     } else {
       // 8 units of 8 bf16 columns; the arithmetic runs on fp32 pairs (FADD2 / FFMA2), which halves the issue slots of this issue-bound loop
       const bool scaled = alpha != 1.0f;
+      float dot = 0.f;   // DIG_EPI_ROWDOT: this row's dot product with the aux tile over the 64-column group
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float f[8];
@@ -158,6 +159,11 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
 #endif
           sts_u4(buf2 + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
         } else {
+          if (MODE == DIG_EPI_ROWDOT) {
+            const uint4 x = lds_u4(buf + off);
+            dot += f[0] * bf16_lo(x.x) + f[1] * bf16_hi(x.x) + f[2] * bf16_lo(x.y) + f[3] * bf16_hi(x.y) + f[4] * bf16_lo(x.z) +
+                   f[5] * bf16_hi(x.z) + f[6] * bf16_lo(x.w) + f[7] * bf16_hi(x.w);
+          }
           if (MODE == DIG_EPI_GELU_BWD) {
             const uint4 x = lds_u4(buf + off);
 #if DIG_GELU_PACKED
@@ -174,6 +180,9 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
           }
           sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
         }
+      }
+      if (MODE == DIG_EPI_ROWDOT) {
+        if (row_base + lane < ep.M && gcol < N) ep.rowdot[(long long)(row_base + lane) * ep.ldrowdot + (gcol >> 6)] = dot;
       }
     }
     if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr) {
@@ -216,9 +225,10 @@ static inline bool tma_epilogue_ok(const dig_gemm_t* g) {
   if (g->row_mask || g->res_row_mod > 0) return false;
   if (g->epilogue == DIG_EPI_RELU_MASK) return false;
   if ((g->N * es) % 16 || (g->ldo * es) % 16 || ((uintptr_t)g->out & 15)) return false;
-  if (g->epilogue == DIG_EPI_GELU || g->epilogue == DIG_EPI_GELU_BWD) {
+  if (g->epilogue == DIG_EPI_GELU || g->epilogue == DIG_EPI_GELU_BWD || g->epilogue == DIG_EPI_ROWDOT) {
     if (g->out_fp32 || (g->ldaux * 2) % 16 || ((uintptr_t)g->aux & 15)) return false;
   }
+  if (g->epilogue == DIG_EPI_ROWDOT && (g->N % 64 != 0 || g->rowdot == nullptr)) return false;
   if (g->residual && (!g->out_fp32 || g->epilogue != DIG_EPI_LINEAR || (g->ldr * 4) % 16 || ((uintptr_t)g->residual & 15))) return false;
   return true;
 }

@@ -37,10 +37,11 @@ class _Gemm(ctypes.Structure):
         ("alpha", ctypes.c_float),
         ("split_k", ctypes.c_int32),
         ("colsum", ctypes.c_void_p),
+        ("rowdot", ctypes.c_void_p), ("ldrowdot", ctypes.c_int64),
     ]
 
 
-EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_RELU_MASK = 0, 1, 2, 3
+EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_RELU_MASK, EPI_ROWDOT = 0, 1, 2, 3, 5
 
 
 _CTYPE = {"int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "float": ctypes.c_float, "int": ctypes.c_int}
@@ -147,7 +148,7 @@ def _req(t, dtype, name):
 
 
 def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=None, res_row_mod=0, row_mask=None,
-         row_mask_value=None, epilogue=EPI_LINEAR, aux=None, alpha=1.0, split_k=1, colsum=None):
+         row_mask_value=None, epilogue=EPI_LINEAR, aux=None, alpha=1.0, split_k=1, colsum=None, rowdot=None):
     """out[M,N] = epilogue(alpha * A.B^T) on tcgen05 (see include/dig_b200.h).
 
     a: bf16 [M,K] (K-major) or [K,M] (a_mn_major); b: bf16 [N,K] or [K,N] (b_mn_major);
@@ -190,6 +191,11 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
     if colsum is not None:
         _req(colsum, torch.float32, "colsum")
         g.colsum = colsum.data_ptr()
+    if rowdot is not None:
+        _req(rowdot, torch.float32, "rowdot")
+        if rowdot.dim() != 2 or rowdot.shape[0] != M or rowdot.shape[1] * 64 < N:
+            raise DigError("rowdot must be fp32 [M, >= N/64], got %s" % (tuple(rowdot.shape),))
+        g.rowdot, g.ldrowdot = rowdot.data_ptr(), rowdot.stride(0)
     if _gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -238,5 +244,24 @@ def attention_bwd(qkv, out, dout, lse, dqkv, heads, scale):
         raise DigError("attention_bwd: bad shapes")
     _check(load().dig_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), rows // 256, heads, scale, _stream()),
            "dig_attention_bwd")
+    count_launch()
+    return dqkv
+
+
+def attention_bwd_d(qkv, dout, lse, dsum, dqkv, heads, scale):
+    """Gradient of attention_fwd w.r.t. qkv with D = rowsum(dout o out) per (token, head) precomputed (fp32 [S*256, heads]; `gemm(...,
+    epilogue=EPI_ROWDOT, aux=out, rowdot=dsum)` on the output-projection dgrad emits it): persistent kernel, `out` is not read."""
+    for t, n in ((qkv, "qkv"), (dout, "dout"), (dqkv, "dqkv")):
+        _req(t, torch.bfloat16, n)
+        if not t.is_contiguous():
+            raise DigError("attention_bwd_d: %s must be contiguous" % n)
+    _req(lse, torch.float32, "lse"); _req(dsum, torch.float32, "dsum")
+    d = heads * 64
+    rows = qkv.shape[0]
+    if qkv.shape != dqkv.shape or qkv.shape[1] != 3 * d or tuple(dout.shape) != (rows, d) or rows % 256 or \
+            tuple(dsum.shape) != (rows, heads) or not dsum.is_contiguous():
+        raise DigError("attention_bwd_d: bad shapes")
+    _check(load().dig_attention_bwd_d(_ptr(qkv), _ptr(dout), _ptr(lse), _ptr(dsum), _ptr(dqkv), rows // 256, heads, scale, _stream()),
+           "dig_attention_bwd_d")
     count_launch()
     return dqkv

@@ -267,6 +267,7 @@ class PretrainStep:
         dln = B.get("bw.dln", (M, d), BF16)
         dat = B.get("bw.dat", (M, d), BF16)
         dqkv = B.get("bw.dqkv", (M, 3 * d), BF16)
+        dsum = B.get("bw.dsum", (M, h), F32)
         # fc2 bias gradient of the last block = column sums of the incoming gradient; for the other blocks it falls out of
         # the LayerNorm-1 backward of the block above (dxsum), like the proj bias gradient out of the LayerNorm-2 backward.
         call("dig_colsum", gb, 0, d, grads[W["blocks"][-1]["name"] + "mlp.fc2.bias"], None, M, d)
@@ -282,8 +283,9 @@ class PretrainStep:
                  grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], grads[nm + "attn.proj.bias"], M, d, 0)
             # ---- attention (F:87-125) ----
             ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
-            ops.gemm(gb, bw["pw"], dat, b_mn_major=True)
-            ops.attention_bwd(a["qkv"], a["att"], dat, a["lse"], dqkv, h, self.scale)
+            # output-projection dgrad; its epilogue also emits D = rowsum(dO o O) per (token, head) for the attention backward
+            ops.gemm(gb, bw["pw"], dat, b_mn_major=True, epilogue=ops.EPI_ROWDOT, aux=a["att"], rowdot=dsum)
+            ops.attention_bwd_d(a["qkv"], dat, a["lse"], dsum, dqkv, h, self.scale)
             dqkvb = B.zeroed("bw.dqkvb%d" % l, (3 * d,), F32, "bwd")
             call("dig_colsum", dqkv, 0, 3 * d, dqkvb, None, M, 3 * d)
             grads[nm + "attn.q_bias"].copy_(dqkvb[:d])

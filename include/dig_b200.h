@@ -34,7 +34,9 @@ enum {
   DIG_EPI_LINEAR = 0,   /* v = alpha*acc (+bias[n]) (row-masked replace) (+residual)                       */
   DIG_EPI_GELU = 1,     /* pre = alpha*acc + bias ; aux[m,n] (bf16) = pre if aux != NULL ; v = gelu_erf(pre) (F:54-55) */
   DIG_EPI_GELU_BWD = 2, /* v = alpha*acc * gelu_erf'(aux[m,n])  (aux: bf16 pre-activation)                 */
-  DIG_EPI_RELU_MASK = 3 /* v = aux[m,n] > 0 ? alpha*acc : 0     (aux: bf16 post-ReLU activation)           */
+  DIG_EPI_RELU_MASK = 3,/* v = aux[m,n] > 0 ? alpha*acc : 0     (aux: bf16 post-ReLU activation)           */
+  DIG_EPI_ROWDOT = 5    /* v = alpha*acc + bias (bf16 out) ; rowdot[m, n/64] = sum over the 64-column group of v * aux[m,n]
+                           (aux: bf16 [M,N]).  Output-projection dgrad: v = dO, aux = O, rowdot = D of the attention backward */
 };
 typedef struct dig_gemm {
   int64_t M, N, K;
@@ -54,6 +56,7 @@ typedef struct dig_gemm {
                                                       that fill the SMs (weight gradients; out zero- or gradient-initialised) */
   float* colsum;                                   /* optional fp32 [N]: colsum[n] += sum_m out[m,n] (bias gradient of the layer
                                                       that produced the GEMM input), NULL to skip                        */
+  float* rowdot; int64_t ldrowdot;                 /* DIG_EPI_ROWDOT: fp32 [M, ldrowdot >= N/64]                            */
 } dig_gemm_t;
 int dig_gemm(const dig_gemm_t* g, void* stream);
 
@@ -68,6 +71,10 @@ int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t num_seqs, 
 /* dqkv : bf16 [num_seqs*256, 3*heads*64] gradient w.r.t. qkv given dout (bf16, layout of out).      */
 int dig_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                       int64_t num_seqs, int32_t heads, float scale, void* stream);
+/* Same gradient with D = rowsum(dout o out) per (token, head) supplied by the caller as fp32 [num_seqs*256, heads] (dig_gemm with
+ * DIG_EPI_ROWDOT emits it from the output-projection dgrad): persistent kernel, operand tiles prefetched across (sequence, head) items. */
+int dig_attention_bwd_d(const void* qkv, const void* dout, const float* lse, const float* dsum, void* dqkv, int64_t num_seqs,
+                        int32_t heads, float scale, void* stream);
 
 /* ---- HBM-bound row / column kernels ---------------------------------------------------------------- */
 /* 4x4/stride-4 patch extraction for the patch-embed GEMM (F:188-195): images fp32 [n,3,32,128] ->

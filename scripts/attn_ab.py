@@ -30,8 +30,17 @@ def fwd(i):
 def bwd(i):
     q, o, l, do, dq = sets[i % 3]
     ops.attention_bwd(q, o, do, l, dq, h, scale)
+dsums = [(st[3].float() * st[1].float()).view(S * 256, h, 64).sum(-1).contiguous() for st in sets]
+def bwd_d(i):
+    q, o, l, do, dq = sets[i % 3]
+    ops.attention_bwd_d(q, do, l, dsums[i % 3], dq, h, scale)
 timeit("attention fwd", fwd, 4.0 * S * h * 256 * 256 * 64)
-timeit("attention bwd", bwd, 10.0 * S * h * 256 * 256 * 64)
+for i in range(3):   # D of the freshly computed outputs
+    dsums[i] = (sets[i][3].float() * sets[i][1].float()).view(S * 256, h, 64).sum(-1).contiguous()
+timeit("attention bwd (one-shot)", bwd, 10.0 * S * h * 256 * 256 * 64)
+dq_ref = sets[0][4].clone()
+timeit("attention bwd (persistent)", bwd_d, 10.0 * S * h * 256 * 256 * 64)
+print("persistent vs one-shot dqkv max diff %.4f" % (sets[0][4].float() - dq_ref.float()).abs().max().item())
 # correctness on the first 4 sequences of set 0
 q, o, l, do, dq = sets[0]
 n = 4 * 256

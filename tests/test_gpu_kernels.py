@@ -86,6 +86,11 @@ def test_gemm_fused_epilogues(ops):
     # the fused bias gradient sums the bf16-rounded dh tile that is staged for the TMA store (as autocast's autograd would)
     assert torch.allclose(cs, dh.float().sum(0), atol=2e-2, rtol=1e-4)
     assert torch.allclose(cs, refb.sum(0), atol=0.15, rtol=2e-3)
+    # ROWDOT: bf16 output + per-64-column-group dot product with aux (D of the attention backward)
+    o3, rd = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.zeros(M, N // 64, device="cuda")
+    ops.gemm(a, wt, o3, b_mn_major=True, epilogue=ops.EPI_ROWDOT, aux=pre, rowdot=rd)
+    assert torch.allclose(o3.float(), acc, atol=3e-2, rtol=1e-2)
+    assert torch.allclose(rd, (acc * pre.float()).view(M, N // 64, 64).sum(-1), atol=5e-2, rtol=1e-2)
     # ReLU mask
     act = torch.relu(rnd(M, N)).to(torch.bfloat16)
     o2 = torch.empty(M, N, device="cuda")
@@ -126,6 +131,11 @@ def test_attention_forward_backward(ops, heads, S):
     dqkv = torch.empty_like(qkv)
     ops.attention_bwd(qkv, out, dout, lse, dqkv, heads, scale)
     assert torch.allclose(dqkv.float(), x.grad, atol=6e-2, rtol=2e-2)   # bf16 P / dS operands
+    # persistent kernel with D = rowsum(dO o O) supplied (as the output-projection dgrad epilogue emits it)
+    dsum = (dout.float() * out.float()).view(S * 256, heads, 64).sum(-1).contiguous()
+    dqkv2 = torch.zeros_like(qkv)
+    ops.attention_bwd_d(qkv, dout, lse, dsum, dqkv2, heads, scale)
+    assert torch.allclose(dqkv2.float(), x.grad, atol=6e-2, rtol=2e-2)
 
 
 @pytest.mark.parametrize("d,gelu", [(384, 0), (512, 0), (192, 1), (192, 0)])
