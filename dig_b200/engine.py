@@ -5,7 +5,7 @@
     the un-normalised view-0 pixels on the fly;
   * the model call is one autograd node running the sm_100a kernels (no autocast: operands are bf16 by
     construction, statistics / losses fp32);
-  * the ~10 blocking `.item()` reads per step (E:123-176) are replaced by ONE packed device->host copy.
+  * the ~10 blocking `.item()` reads per step (E:123-176) are replaced by ONE packed device->host copy, consumed one step late.
 """
 import math
 import sys
@@ -81,6 +81,29 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
     else:
         w = np.zeros(n_it)
 
+    pinned = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending = None
+
+    def consume(rec):
+        ev, slot, loss_scale_value, lr_max, lr_min, wd, = rec
+        ev.synchronize()
+        packed = slot.tolist()
+        loss_value = packed[0]
+        if not math.isfinite(loss_value):                                                             # E:148-150
+            print("Loss is {}, stopping training".format(loss_value))
+            sys.exit(1)
+        metric_logger.update(loss_contrast=packed[1], q1_acc1=packed[3], q1_acc5=packed[4], q2_acc1=packed[5], q2_acc5=packed[6],
+                             loss_pixel=packed[2], loss=loss_value, loss_scale=loss_scale_value)
+        metric_logger.update(lr=lr_max, min_lr=lr_min, weight_decay=wd, grad_norm=packed[7])
+        if log_writer is not None:
+            log_writer.update(loss=loss_value, head="loss")
+            log_writer.update(loss_scale=loss_scale_value, head="opt")
+            log_writer.update(lr=lr_max, head="opt")
+            log_writer.update(min_lr=lr_min, head="opt")
+            log_writer.update(weight_decay=wd, head="opt")
+            log_writer.update(grad_norm=packed[7], head="opt")
+            log_writer.set_step()
+
     for step, (batch, text, text_lens) in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
         it = start_steps + step
         if lr_schedule_values is not None or wd_schedule_values is not None:                      # E:60-66
@@ -108,27 +131,25 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
         grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=model.parameters(), create_graph=False)
         loss_scale_value = loss_scaler.state_dict()["scale"]
 
-        # one packed device->host read per step (the reference blocks ~10 times, E:123-176)
+        # One packed device->host read per step (the reference blocks ~10 times, E:123-176), and it is consumed ONE STEP LATE: the copy
+        # goes to a pinned buffer behind an event, and the meters / finite check of step n run after step n+1 has been enqueued, so the
+        # host never drains the GPU queue inside the epoch.  Values, averages and the returned dict are unchanged; log lines lag a step.
         packed = torch.stack([loss.detach().float().reshape(()), contra.detach().float().reshape(()), loss_pixel.detach().reshape(()),
                               out["q1_acc1"].reshape(()), out["q1_acc5"].reshape(()), out["q2_acc1"].reshape(()),
-                              out["q2_acc5"].reshape(()), grad_norm.to(loss.device).float().reshape(())]).tolist()
-        loss_value = packed[0]
-        if not math.isfinite(loss_value):                                                             # E:148-150
-            print("Loss is {}, stopping training".format(loss_value))
-            sys.exit(1)
-        metric_logger.update(loss_contrast=packed[1], q1_acc1=packed[3], q1_acc5=packed[4], q2_acc1=packed[5], q2_acc5=packed[6],
-                             loss_pixel=packed[2], loss=loss_value, loss_scale=loss_scale_value)
+                              out["q2_acc5"].reshape(()), grad_norm.to(loss.device).float().reshape(())])
+        slot = pinned[step & 1]
+        slot.copy_(packed, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
         lrs = [g["lr"] for g in optimizer.param_groups]
         wds = [g["weight_decay"] for g in optimizer.param_groups if g["weight_decay"] > 0]
-        metric_logger.update(lr=max(lrs), min_lr=min(lrs), weight_decay=wds[-1] if wds else None, grad_norm=packed[7])
-        if log_writer is not None:
-            log_writer.update(loss=loss_value, head="loss")
-            log_writer.update(loss_scale=loss_scale_value, head="opt")
-            log_writer.update(lr=max(lrs), head="opt")
-            log_writer.update(min_lr=min(lrs), head="opt")
-            log_writer.update(weight_decay=wds[-1] if wds else None, head="opt")
-            log_writer.update(grad_norm=packed[7], head="opt")
-            log_writer.set_step()
+        this = (ev, slot, loss_scale_value, max(lrs), min(lrs), wds[-1] if wds else None)
+        if pending is not None:
+            consume(pending)
+        pending = this
+        if step == 0:          # the logger prints after the first iteration: give it real values (one synchronising read per epoch)
+            consume(pending)
+            pending = None
         if lr_scheduler is not None:
             lr_scheduler.step_update(start_steps + step)
         if step >= 1 and step % (args.eval_freq * 10) == 0 and getattr(args, "output_dir", None):
@@ -137,6 +158,8 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
                        loss_scaler=loss_scaler, epoch="{0}_{1}".format(epoch, step))
         sys.stdout.flush()
 
+    if pending is not None:
+        consume(pending)
     metric_logger.synchronize_between_processes()
     print("Averaged stats:", metric_logger)
     return {k: meter.global_avg for k, meter in metric_logger.meters.items()}
