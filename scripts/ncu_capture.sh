@@ -12,13 +12,13 @@ cap() {  # name regex skip
   ncu -i gpurun_out/${TAG}_$1.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/${TAG}_$1.source.csv.gz
   rm -f gpurun_out/${TAG}_$1.ncu-rep
 }
-cap fc1_gelu   'gemm_bf16_tcgen05<[^,]*128, [^,]*0, [^,]*0, [^,]*1, [^,]*0, [^,]*1>' 14
+cap fc1_gelu   'gemm2_bf16_tcgen05<[^,]*256, [^,]*0, [^,]*0, [^,]*1, [^,]*0, [^,]*1>' 14
 cap gelu_bwd   'gemm2_bf16_tcgen05<[^,]*256, [^,]*0, [^,]*1, [^,]*2, [^,]*0, [^,]*1>' 5
-cap wgrad      'gemm_bf16_tcgen05<[^,]*128, [^,]*1, [^,]*1, [^,]*4, [^,]*1, [^,]*1>' 20 4
+cap wgrad      'gemm2_bf16_tcgen05<[^,]*256, [^,]*1, [^,]*1, [^,]*4, [^,]*1, [^,]*1>' 20 3
 cap res_f32    'gemm2_bf16_tcgen05<[^,]*192, [^,]*0, [^,]*0, [^,]*0, [^,]*1, [^,]*1>' 30 2
 cap qkv        'gemm2_bf16_tcgen05<[^,]*192, [^,]*0, [^,]*0, [^,]*0, [^,]*0, [^,]*1>' 14
 cap dgrad      'gemm2_bf16_tcgen05<[^,]*128, [^,]*0, [^,]*1, [^,]*0, [^,]*0, [^,]*1>' 6
-cap attn_fwd   'attn_fwd_kernel' 14
-cap attn_bwd   'attn_bwd_kernel' 5
+cap attn_fwd   'attn_fwd_persist_kernel' 14
+cap attn_bwd   'attn_bwd_persist_kernel' 5
 cap ln_bwd     'layernorm_bwd_kernel' 5
 cap ln_fwd     'layernorm_fwd_kernel' 30
