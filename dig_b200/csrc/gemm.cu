@@ -86,7 +86,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -121,11 +121,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (the whole warp walks the loop, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t smem_s = smem_u32(smem);
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int split = w / (num_n * num_m);
         const int kb0 = split * kb_per_split;
@@ -138,18 +139,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStage);
+          const uint32_t sa = smem_s + stage * S::kStage;
           const uint32_t sb = sa + S::kStageA;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_sdesc_sw128(sa + k * 2048, 8192, 1024) : make_sdesc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_sdesc_sw128(sb + k * 2048, 8192, 1024) : make_sdesc_sw128(sb + k * 32, 16, 1024);
-            tc_mma_ss(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN ? make_sdesc_sw128(sa + k * 2048, 8192, 1024) : make_sdesc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t db = B_MN ? make_sdesc_sw128(sb + k * 2048, 8192, 1024) : make_sdesc_sw128(sb + k * 32, 16, 1024);
+              tc_mma_ss(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete
+        if (elect_one()) tc_commit(&tmem_full[acc]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {

@@ -25,7 +25,7 @@ struct Gemm2Smem {
   static constexpr int kStageA = 128 * BK * 2;
   static constexpr int kStageB = (BN / 2) * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 128) ? 6 : (TMA_EPI ? 4 : 5);
+  static constexpr int kStages = (BN == 128) ? 6 : (BN == 192 ? 5 : (TMA_EPI ? 4 : 5));
   static constexpr int kEpi = TMA_EPI ? kEpiTmaBytes : kEpiWarps * 32 * 32 * 4;
   static constexpr int kColsum = 2048 * 4;
   static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 + 512;
@@ -135,11 +135,43 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   __syncthreads();
   cluster_sync_all();  // peer barriers are initialised before anyone arrives on them remotely
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs, own halves) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs, own halves; the whole warp walks the loop, one elected lane issues) ==========
+    // Activation operands stream from DRAM (each tile is first touched here), and the shared-memory ring holds only ~1 us of MMA work:
+    // an L2 prefetch iterator runs kPfDist k-blocks (possibly one work item) ahead of the loads so those find their lines in L2.
+    {
+      constexpr bool kPrefetchB = A_MN && B_MN;   // weight gradients: both operands are activations; otherwise B = weights (L2-resident)
+      const int pf_dist = ep.dbg >= 10 ? ep.dbg - 10 : 0;   // off by default: measured 10-45 % SLOWER with it (scripts/gemm_ab.py, DIG_GEMM_DBG=10+distance)
+      int pw = cluster_id, pkb = 0, pkb1 = 0;
+      auto pf_set = [&]() {
+        if (pw < num_work) {
+          const int split = pw / (num_n * num_m);
+          pkb = split * kb_per_split;
+          pkb1 = min(pkb + kb_per_split, num_kb);
+        }
+      };
+      auto pf_issue = [&]() {
+        if (pw >= num_work) return;
+        const int m0 = ((pw / num_n) % num_m) * 256 + (int)rank * 128;
+        const int n0 = (pw % num_n) * BN + (int)rank * HB;
+        if (elect_one()) {
+          if (!A_MN) tma_prefetch_l2_2d(&tma_a, pkb * BK, m0);
+          else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_prefetch_l2_2d(&tma_a, m0 + j * 64, pkb * BK);
+          }
+          if (kPrefetchB) {
+#pragma unroll
+            for (int j = 0; j < HB / 64; ++j) tma_prefetch_l2_2d(&tma_b, n0 + j * 64, pkb * BK);
+          }
+        }
+        __syncwarp();
+        if (++pkb == pkb1) { pw += num_clusters; pf_set(); }
+      };
+      pf_set();
+      for (int i = 0; i < pf_dist; ++i) pf_issue();
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
@@ -154,30 +186,35 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStage;
           uint8_t* sb = sa + S::kStageA;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::kStage);
-          else mbar_arrive_remote(&full_bar[stage], 0);
-          if (!A_MN) {
-            tma_load_2d_2sm(sa, &tma_a, &full_bar[stage], kb * BK, m0);
-          } else {
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::kStage);
+            else mbar_arrive_remote(&full_bar[stage], 0);
+            if (!A_MN) {
+              tma_load_2d_2sm(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
-          }
-          if (!B_MN) {
-            tma_load_2d_2sm(sb, &tma_b, &full_bar[stage], kb * BK, n0);
-          } else {
+              for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_2sm(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < HB / 64; ++j) tma_load_2d_2sm(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+              for (int j = 0; j < HB / 64; ++j) tma_load_2d_2sm(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * BK);
+            }
           }
+          __syncwarp();
+          if (pf_dist > 0) pf_issue();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA; the whole warp walks the loop, one elected lane issues) =====================
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t smem_s = smem_u32(smem);
       for (int w = cluster_id; w < num_work; w += num_clusters, ++it) {
         const int split = w / (num_n * num_m);
         const int kb0 = split * kb_per_split;
@@ -190,18 +227,22 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStage);
+          const uint32_t sa = smem_s + stage * S::kStage;
           const uint32_t sb = sa + S::kStageA;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_sdesc_sw128(sa + k * 2048, 8192, 1024) : make_sdesc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_sdesc_sw128(sb + k * 2048, 8192, 1024) : make_sdesc_sw128(sb + k * 32, 16, 1024);
-            tc_mma_ss_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN ? make_sdesc_sw128(sa + k * 2048, 8192, 1024) : make_sdesc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t db = B_MN ? make_sdesc_sw128(sb + k * 2048, 8192, 1024) : make_sdesc_sw128(sb + k * 32, 16, 1024);
+              tc_mma_ss_2sm(d_tmem, da, db, kIdesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_2sm(&empty_bar[stage]);
           }
-          tc_commit_2sm(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit_2sm(&tmem_full[acc]);
+        if (elect_one()) tc_commit_2sm(&tmem_full[acc]);
+        __syncwarp();
       }
     }
   } else {
