@@ -185,9 +185,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 // O / sum -> HBM (threads).  The tile-to-tile prologue, TMA latency and MMA latency of the one-shot kernel above are hidden behind the
 // other slot's softmax, which is the MUFU-bound critical resource.
 // ------------------------------------------------------------------------------------------------
-#ifndef DIG_ATTN_EVT
-#define DIG_ATTN_EVT 1
-#endif
 #ifndef DIG_ATTN_STAGGER
 #define DIG_ATTN_STAGGER 3000
 #endif
@@ -226,8 +223,8 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * kHd;
-  long long* const dbg = (blockIdx.x == 0 && lane == 0 && (warp == 1 || (warp & 3) == 0)) ? g_attn_dbg : nullptr;
-  if (dbg != nullptr && warp == 1) {
+  long long* const dbg = (blockIdx.x == 0 && (warp == 1 || (lane == 0 && (warp & 3) == 0))) ? g_attn_dbg : nullptr;
+  if (dbg != nullptr && warp == 1 && lane == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     dbg[11 * 8 + 0] = clock64();
@@ -252,7 +249,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_holder;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
   constexpr uint32_t kColO = 192;
 
   if (warp == 0) {
@@ -274,103 +271,71 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tma_load_2d(base + 81920, &tm_qkv, &v_full[b], 2 * d + head * kHd, row0 + 128);
       }
     }
-#if DIG_ATTN_EVT
   } else if (warp == 1) {
-    if (lane == 0) {
-      // Event-driven issue: each slot is its own S -> (softmax) -> PV pipeline.  The thread probes (mbarrier.test_wait, non-blocking)
-      // the barriers the slot's next action needs and issues whichever is ready, and slot 1 is started half a period late, so one
-      // slot's MMAs, O drain and barrier round trips hide behind the other slot's exp2 work instead of both slots hitting the MUFU
-      // pipe -- and then both leaving it -- together (measured with the clock stamps: 48% MUFU duty in lock-step).
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
-      const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      int cnt[2] = {0, 0};      // items completed (PV issued) per slot
-      int stage[2] = {0, 0};    // 0: S to issue, 1: PV to issue
-      int pv_issued[2] = {0, 0};  // per K/V buffer: slots whose PV of the buffer's current item has been issued
-      bool first_s0 = false;
-      long long t_first = 0;
-      while (cnt[0] < my_items || cnt[1] < my_items) {
+    // Event-driven issue: each slot is its own S -> (softmax) -> PV pipeline.  The warp probes (mbarrier.test_wait, non-blocking; lane 0
+    // probes, a vote makes the result warp-uniform) the barriers the slot's next action needs and issues whichever is ready, and slot 1
+    // is started half a period late, so one slot's MMAs, O drain and barrier round trips hide behind the other slot's exp2 work instead
+    // of both slots hitting the MUFU pipe -- and then both leaving it -- together (clock stamps: 48 % MUFU duty in lock-step).
+    // The whole warp walks the loop and ONE ELECTED lane issues: with the loop inside `if (lane == 0)` ptxas wraps every tcgen05.mma in an
+    // ELECT / R2UR waterfall (~20 instructions), which held the PV products (16 x N=64) at 80 clocks per instruction.
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+    const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t smem_s = smem_u32(smem);
+    int cnt0 = 0, cnt1 = 0;          // items completed (PV issued) per slot
+    int stage0 = 0, stage1 = 0;      // 0: S to issue, 1: PV to issue
+    int pv_issued0 = 0, pv_issued1 = 0;  // per K/V buffer: slots whose PV of the buffer's current item has been issued
+    bool first_s0 = false;
+    long long t_first = 0;
+    while (cnt0 < my_items || cnt1 < my_items) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int n = cnt[s];
-          if (n >= my_items) continue;
-          const int b = n & 1;
-          const uint32_t u = (uint32_t)(n >> 1) & 1u, np = (uint32_t)n & 1u;
-          const uint32_t base = smem_u32(smem + b * kFwdPBuf);
-          if (stage[s] == 0) {
-            if (!mbar_test_wait(&qk_full[b], u) || !mbar_test_wait(&s_free[s], np ^ 1u)) continue;
-            if (s == 1 && n == 0 && !first_s0) continue;                                   // slot 0 leads ...
-            if (s == 1 && n == 0 && clock64() - t_first < kAttnStagger) continue;          // ... by about half a slot period
-            if (s == 0 && n == 0) { first_s0 = true; t_first = clock64(); }
-            tc_fence_after();
+      for (int s = 0; s < 2; ++s) {
+        const int n = s == 0 ? cnt0 : cnt1;
+        const int stg = s == 0 ? stage0 : stage1;
+        if (n >= my_items) continue;
+        const int b = n & 1;
+        const uint32_t u = (uint32_t)(n >> 1) & 1u, np = (uint32_t)n & 1u;
+        const uint32_t base = smem_s + b * kFwdPBuf;
+        bool ok = false;
+        if (lane == 0) {
+          if (stg == 0) {
+            ok = mbar_test_wait(&qk_full[b], u) && mbar_test_wait(&s_free[s], np ^ 1u);
+            if (s == 1 && n == 0) ok = ok && first_s0 && (clock64() - t_first >= kAttnStagger);   // slot 0 leads by half a period
+          } else {
+            ok = mbar_test_wait(&p_full[s], np) && mbar_test_wait(&v_full[b], u);
+          }
+        }
+        if (!__any_sync(0xffffffffu, ok)) continue;
+        tc_fence_after();
+        if (stg == 0) {
+          if (s == 0 && n == 0) { first_s0 = true; t_first = clock64(); }
+          if (elect_one()) {
             DIG_STAMP(0, n, 1 + s);
 #pragma unroll
             for (int k = 0; k < kHd / 16; ++k)
               tc_mma_ss(tmem + s * 256, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024),
                         make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s, k > 0);
             tc_commit(&s_full[s]);
-            stage[s] = 1;
-          } else {
-            if (!mbar_test_wait(&p_full[s], np) || !mbar_test_wait(&v_full[b], u)) continue;
-            tc_fence_after();
+          }
+          __syncwarp();
+          if (s == 0) stage0 = 1; else stage1 = 1;
+        } else {
+          const int pv = (b == 0 ? pv_issued0 : pv_issued1) + 1;
+          if (elect_one()) {
             DIG_STAMP(0, n, 4 + s);
 #pragma unroll
             for (int k = 0; k < kTok / 16; ++k)
               tc_mma_ts(tmem + s * 256 + kColO, tmem + s * 256 + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o,
                         k > 0);
             tc_commit(&o_full[s]);
-            if (++pv_issued[b] == 2) {  // both slots are through with this item's Q/K/V: hand the buffer back to the producer
-              tc_commit(&kv_empty[b]);
-              pv_issued[b] = 0;
-            }
-            stage[s] = 0;
-            cnt[s] = n + 1;
+            if (pv == 2) tc_commit(&kv_empty[b]);  // both slots are through with this item's Q/K/V: hand the buffer back to the producer
           }
+          __syncwarp();
+          if (b == 0) pv_issued0 = pv == 2 ? 0 : pv; else pv_issued1 = pv == 2 ? 0 : pv;
+          if (s == 0) { stage0 = 0; cnt0 = n + 1; } else { stage1 = 0; cnt1 = n + 1; }
         }
       }
     }
-#else
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
-      int n = 0;
-      for (int w = blockIdx.x; w < num_items; w += gridDim.x, ++n) {
-        const int b = n & 1;
-        const uint32_t u = (uint32_t)(n >> 1) & 1u, np = (uint32_t)n & 1u;
-        const uint32_t base = smem_u32(smem + b * kFwdPBuf);
-        mbar_wait(&qk_full[b], u);
-        tc_fence_after();
-        DIG_STAMP(0, n, 0);
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          mbar_wait(&s_free[s], np ^ 1u);
-          tc_fence_after();
-          DIG_STAMP(0, n, 1 + s);
-#pragma unroll
-          for (int k = 0; k < kHd / 16; ++k)
-            tc_mma_ss(tmem + s * 256, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024),
-                      make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s, k > 0);
-          tc_commit(&s_full[s]);
-        }
-        DIG_STAMP(0, n, 3);
-        mbar_wait(&v_full[b], u);
-        tc_fence_after();
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          mbar_wait(&p_full[s], np);
-          tc_fence_after();
-          DIG_STAMP(0, n, 4 + s);
-#pragma unroll
-          for (int k = 0; k < kTok / 16; ++k)
-            tc_mma_ts(tmem + s * 256 + kColO, tmem + s * 256 + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0);
-          tc_commit(&o_full[s]);
-        }
-        tc_commit(&kv_empty[b]);  // both PV products have read V (and, before them, both S products Q and K)
-        DIG_STAMP(0, n, 6);
-      }
-    }
-#endif
   } else {
     const int s = (warp - 2) >> 2;
     const int quarter = warp & 3;
@@ -484,7 +449,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (dbg != nullptr && warp == 1) {
+  if (dbg != nullptr && warp == 1 && lane == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     dbg[11 * 8 + 1] = clock64();
@@ -786,7 +751,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_holder;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
   constexpr uint32_t cS = 0, cdP = 128, cdV = 256, cdK = 320, cdQ = 384;
 
   if (warp == 9) {
@@ -813,8 +778,8 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       }
     }
   } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && total > 0) {
+    // ===================== MMA issuer (the whole warp walks the loop, one elected lane issues: no per-instruction waterfall) ==========
+    if (total > 0) {
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, false, false);
       constexpr uint32_t id_tt = make_idesc_bf16(128, 64, true, true);   // dV, dK: A = P^T / dS^T (MN-major), B MN-major
       constexpr uint32_t id_q = make_idesc_bf16(128, 64, false, true);   // dQ: A = dS (K-major), B = K (MN-major)
@@ -826,13 +791,16 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         mbar_wait(&kv_full[j], (uint32_t)n & 1u);
         tc_fence_after();
         const uint32_t aQ = base + kBwdQdO + sl * 32768, adO = aQ + 16384, aK = base + kBwdKV + j * 32768, aV = aK + 16384;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_ss(tmem + cS, make_sdesc_sw128(aQ + k * 32, 16, 1024), make_sdesc_sw128(aK + k * 32, 16, 1024), id_s, k > 0);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_ss(tmem + cS, make_sdesc_sw128(aQ + k * 32, 16, 1024), make_sdesc_sw128(aK + k * 32, 16, 1024), id_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_ss(tmem + cdP, make_sdesc_sw128(adO + k * 32, 16, 1024), make_sdesc_sw128(aV + k * 32, 16, 1024), id_s, k > 0);
-        tc_commit(bar_sdp);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_ss(tmem + cdP, make_sdesc_sw128(adO + k * 32, 16, 1024), make_sdesc_sw128(aV + k * 32, 16, 1024), id_s, k > 0);
+          tc_commit(bar_sdp);
+        }
+        __syncwarp();
       };
       issue_sdp(0);
       for (int g = 0; g < total; ++g) {
@@ -841,23 +809,26 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         mbar_wait(bar_pds, (uint32_t)g & 1u);
         tc_fence_after();
         if (g + 1 < total) issue_sdp(g + 1);   // the next block's scores go ahead of this block's gradient products
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
-          tc_mma_ss(tmem + cdV, make_sdesc_sw128(aP + k * 2048, 16384, 1024), make_sdesc_sw128(adO + k * 2048, 8192, 1024), id_tt,
-                    (i > 0 || k > 0));
+          for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
+            tc_mma_ss(tmem + cdV, make_sdesc_sw128(aP + k * 2048, 16384, 1024), make_sdesc_sw128(adO + k * 2048, 8192, 1024), id_tt,
+                      (i > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
-          tc_mma_ss(tmem + cdK, make_sdesc_sw128(adS + k * 2048, 16384, 1024), make_sdesc_sw128(aQ + k * 2048, 8192, 1024), id_tt,
-                    (i > 0 || k > 0));
+          for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
+            tc_mma_ss(tmem + cdK, make_sdesc_sw128(adS + k * 2048, 16384, 1024), make_sdesc_sw128(aQ + k * 2048, 8192, 1024), id_tt,
+                      (i > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dQ_i += dS K_j     (reduction over 128 keys)
-          tc_mma_ss(tmem + cdQ + i * 64, make_sdesc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    make_sdesc_sw128(aK + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0));
-        tc_commit(bar_mma);
-        // ring releases: a commit arrives once every MMA issued so far (including the S,dP of block g+1 above) has completed
-        if (it == 1) tc_commit(&kv_empty[0]);
-        else if (it == 2) tc_commit(&qdo_empty[qdo_slot(g)]);             // (Q_0 | dO_0): blocks 0 and 2
-        else if (it == 3) { tc_commit(&qdo_empty[sl]); tc_commit(&kv_empty[1]); }
+          for (int k = 0; k < 8; ++k)  // dQ_i += dS K_j     (reduction over 128 keys)
+            tc_mma_ss(tmem + cdQ + i * 64, make_sdesc_sw128(adS + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_sdesc_sw128(aK + k * 2048, 8192, 1024), id_q, (j > 0 || k > 0));
+          tc_commit(bar_mma);
+          // ring releases: a commit arrives once every MMA issued so far (including the S,dP of block g+1 above) has completed
+          if (it == 1) tc_commit(&kv_empty[0]);
+          else if (it == 2) tc_commit(&qdo_empty[sl]);                          // (Q_0 | dO_0): blocks 0 and 2
+          else if (it == 3) { tc_commit(&qdo_empty[sl]); tc_commit(&kv_empty[1]); }
+        }
+        __syncwarp();
       }
     }
   } else {
