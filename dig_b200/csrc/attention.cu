@@ -214,12 +214,14 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFwdPBuf + 2 * 16384);   // after the two 16 KB output staging tiles
   uint64_t* qk_full = bars + 0;    // [2 buffers] TMA -> MMA
   uint64_t* v_full = bars + 2;     // [2 buffers] TMA -> MMA
-  uint64_t* kv_empty = bars + 4;   // [2 buffers] MMA -> TMA
+  uint64_t* v_empty = bars + 4;    // [2 buffers] MMA -> TMA: both PV products have read V
   uint64_t* s_full = bars + 6;     // [2 slots]   MMA -> softmax
   uint64_t* p_full = bars + 8;     // [2 slots]   softmax -> MMA (128 arrivals)
   uint64_t* o_full = bars + 10;    // [2 slots]   MMA -> softmax
   uint64_t* s_free = bars + 12;    // [2 slots]   softmax -> MMA (128 arrivals): O drained, the slot's TMEM may be overwritten
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* k_empty = bars + 14;   // [2 buffers] MMA -> TMA: both S products have read K (released a softmax phase before V)
+  uint64_t* q_empty = bars + 16;   // [2 slots][2 buffers] MMA -> TMA: the slot's S product has read its Q tile
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * kHd;
@@ -237,7 +239,10 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qk_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&q_empty[2 + i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&o_full[i], 1);
@@ -260,12 +265,17 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const uint32_t u = (uint32_t)(n >> 1) & 1u;
         const int head = w % heads, row0 = (w / heads) * kTok;
         uint8_t* base = smem + b * kFwdPBuf;
-        mbar_wait(&kv_empty[b], u ^ 1u);
+        // Q tiles and K are handed back right after the S products (a whole softmax phase before V), so most of the next-but-one
+        // item's bytes are requested early: the 2-deep buffer ring then covers the ~1.8 us it takes one SM to pull 96 KB from HBM.
+        mbar_wait(&q_empty[b], u ^ 1u);          // slot 0's S of the item two back is done: that item's qk_full phase has completed
         mbar_expect_tx(&qk_full[b], 65536);
         tma_load_2d(base, &tm_qkv, &qk_full[b], head * kHd, row0);
+        mbar_wait(&q_empty[2 + b], u ^ 1u);
         tma_load_2d(base + 16384, &tm_qkv, &qk_full[b], head * kHd, row0 + 128);
+        mbar_wait(&k_empty[b], u ^ 1u);
         tma_load_2d(base + 32768, &tm_qkv, &qk_full[b], d + head * kHd, row0);
         tma_load_2d(base + 49152, &tm_qkv, &qk_full[b], d + head * kHd, row0 + 128);
+        mbar_wait(&v_empty[b], u ^ 1u);
         mbar_expect_tx(&v_full[b], 32768);
         tma_load_2d(base + 65536, &tm_qkv, &v_full[b], 2 * d + head * kHd, row0);
         tma_load_2d(base + 81920, &tm_qkv, &v_full[b], 2 * d + head * kHd, row0 + 128);
@@ -284,7 +294,8 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const uint32_t smem_s = smem_u32(smem);
     int cnt0 = 0, cnt1 = 0;          // items completed (PV issued) per slot
     int stage0 = 0, stage1 = 0;      // 0: S to issue, 1: PV to issue
-    int pv_issued0 = 0, pv_issued1 = 0;  // per K/V buffer: slots whose PV of the buffer's current item has been issued
+    int pv_issued0 = 0, pv_issued1 = 0;  // per buffer: slots whose PV of the buffer's current item has been issued
+    int s_issued0 = 0, s_issued1 = 0;    // per buffer: slots whose S of the buffer's current item has been issued
     bool first_s0 = false;
     long long t_first = 0;
     while (cnt0 < my_items || cnt1 < my_items) {
@@ -309,6 +320,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tc_fence_after();
         if (stg == 0) {
           if (s == 0 && n == 0) { first_s0 = true; t_first = clock64(); }
+          const int si = (b == 0 ? s_issued0 : s_issued1) + 1;
           if (elect_one()) {
             DIG_STAMP(0, n, 1 + s);
 #pragma unroll
@@ -316,8 +328,11 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
               tc_mma_ss(tmem + s * 256, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024),
                         make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s, k > 0);
             tc_commit(&s_full[s]);
+            tc_commit(&q_empty[2 * s + b]);
+            if (si == 2) tc_commit(&k_empty[b]);
           }
           __syncwarp();
+          if (b == 0) s_issued0 = si == 2 ? 0 : si; else s_issued1 = si == 2 ? 0 : si;
           if (s == 0) stage0 = 1; else stage1 = 1;
         } else {
           const int pv = (b == 0 ? pv_issued0 : pv_issued1) + 1;
@@ -328,7 +343,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
               tc_mma_ts(tmem + s * 256 + kColO, tmem + s * 256 + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o,
                         k > 0);
             tc_commit(&o_full[s]);
-            if (pv == 2) tc_commit(&kv_empty[b]);  // both slots are through with this item's Q/K/V: hand the buffer back to the producer
+            if (pv == 2) tc_commit(&v_empty[b]);   // both slots are through with this item's V
           }
           __syncwarp();
           if (b == 0) pv_issued0 = pv == 2 ? 0 : pv; else pv_issued1 = pv == 2 ? 0 : pv;

@@ -20,14 +20,15 @@ namespace dig {
 static constexpr int BK = 64;
 static constexpr int kGemm2Threads = 64 + kEpiWarps * 32;
 
-template <int BN, bool TMA_EPI>
+template <int BN, bool TMA_EPI, int MODE>
 struct Gemm2Smem {
   static constexpr int kStageA = 128 * BK * 2;
   static constexpr int kStageB = (BN / 2) * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 128) ? 6 : (BN == 192 ? 5 : (TMA_EPI ? 4 : 5));
   static constexpr int kEpi = TMA_EPI ? kEpiTmaBytes : kEpiWarps * 32 * 32 * 4;
-  static constexpr int kColsum = 2048 * 4;
+  static constexpr int kColsum = (MODE == DIG_EPI_GELU_BWD) ? 2048 * 4 : 0;   // per-CTA column-sum scratch: only the GELU' epilogue uses it
+  // as many ring stages as fit in 227 KB: the ring holds only ~1 us of MMA work and every tile's operands are first touched from DRAM
+  static constexpr int kStages = (232448 - 1024 - 512 - kEpi - kColsum) / kStage > 6 ? 6 : (232448 - 1024 - 512 - kEpi - kColsum) / kStage;
   static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 + 512;
 };
 
@@ -82,7 +83,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux, GemmEpilogue ep, int M, int N,
                    int K, int split_k, int kb_per_split) {
-  using S = Gemm2Smem<BN, TMA_EPI>;
+  using S = Gemm2Smem<BN, TMA_EPI, MODE>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t kIdesc = make_idesc_bf16(256, BN, A_MN, B_MN);
@@ -294,7 +295,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
 template <int BN, bool A_MN, bool B_MN, int MODE, bool OUT_F32, bool TMA_EPI>
 static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
-  using S = Gemm2Smem<BN, TMA_EPI>;
+  using S = Gemm2Smem<BN, TMA_EPI, MODE>;
   CUtensorMap ta, tb;
   int rc;
   if (!g->a_mn_major) rc = make_tmap_bf16_2d(&ta, g->A, (uint64_t)g->M, (uint64_t)g->K, (uint64_t)g->lda, 128, BK);
