@@ -259,14 +259,54 @@ class PretrainStep:
         return x, dict(a0=a0, acts=acts, mask=mask_u8)
 
     def _encoder_bwd(self, W, sv, g, gb, grads):
-        """g fp32 / gb bf16 [M,d]: gradient w.r.t. the encoder output.  Accumulates parameter gradients into `grads`."""
+        """g fp32 / gb bf16 [M,d]: gradient w.r.t. the encoder output.  Accumulates parameter gradients into `grads`.
+
+        The activation-gradient chain (GELU' dgrad -> fc1 dgrad -> LN2 bwd -> proj dgrad -> attention bwd -> qkv dgrad -> LN1 bwd) runs on
+        the current stream; the weight-gradient GEMMs and the qkv bias column sums are off that chain and go to the side stream, so they
+        fill in next to the chain's HBM-bound kernels.  The scratch tensors both streams touch (gb, dh, dqkv) rotate through small rings;
+        before the chain overwrites a ring slot it waits for the event its last side-stream reader recorded."""
         B = self.bufs
         M, d, h = g.shape[0], self.d, self.heads
-        S = M // TOK
-        dh = B.get("bw.dh", (M, 4 * d), BF16)
+        cur = torch.cuda.current_stream()
+        side = self._side if self._two_streams else cur
+        two = side is not cur
+        ring = {"gb": 4, "dh": 2, "dqkv": 2} if two else {"gb": 1, "dh": 1, "dqkv": 1}
+        shapes = {"gb": (M, d), "dh": (M, 4 * d), "dqkv": (M, 3 * d)}
+        bufs = {k: [B.get("bw.%s%d" % (k, i), shapes[k], BF16) for i in range(n)] for k, n in ring.items()}
+        busy = {k: [None] * n for k, n in ring.items()}    # event recorded on the side stream after the slot's last reader there
+        nxt = {k: 0 for k in ring}
+
+        def take(kind):
+            """Next ring slot of `kind` for the chain to write: waits for its pending side-stream readers."""
+            i = nxt[kind]
+            nxt[kind] = (i + 1) % ring[kind]
+            if busy[kind][i] is not None:
+                cur.wait_event(busy[kind][i])
+                busy[kind][i] = None
+            return i, bufs[kind][i]
+
+        def on_side(fn, reads):
+            """Run fn() on the side stream once everything enqueued on the chain so far is done; mark the ring slots it reads busy."""
+            if not two:
+                fn()
+                return
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fn()
+                done = torch.cuda.Event()
+                done.record(side)
+            for kind, i in reads:
+                busy[kind][i] = done
+
+        if two:
+            side.wait_stream(cur)          # zeroed gradient buffer, head gradients
+        gi, gb0 = take("gb")
+        gb0.copy_(gb)                       # incoming gradient into ring slot 0 (the caller's buffer stays untouched)
+        gb = gb0
         dln = B.get("bw.dln", (M, d), BF16)
         dat = B.get("bw.dat", (M, d), BF16)
-        dqkv = B.get("bw.dqkv", (M, 3 * d), BF16)
         dsum = B.get("bw.dsum", (M, h), F32)
         # fc2 bias gradient of the last block = column sums of the incoming gradient; for the other blocks it falls out of
         # the LayerNorm-1 backward of the block above (dxsum), like the proj bias gradient out of the LayerNorm-2 backward.
@@ -275,26 +315,41 @@ class PretrainStep:
             bw, a = W["blocks"][l], sv["acts"][l]
             nm = bw["name"]
             # ---- MLP (F:53-60) ----
-            ops.gemm(gb, a["hpost"], grads[nm + "mlp.fc2.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
+            hi, dh = take("dh")
             ops.gemm(gb, bw["f2w"], dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=a["hpre"], colsum=grads[nm + "mlp.fc1.bias"])
-            ops.gemm(dh, a["ln2"], grads[nm + "mlp.fc1.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
+
+            def mlp_wgrads(gb=gb, dh=dh, a=a, nm=nm):
+                ops.gemm(gb, a["hpost"], grads[nm + "mlp.fc2.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
+                ops.gemm(dh, a["ln2"], grads[nm + "mlp.fc1.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
+            on_side(mlp_wgrads, [("gb", gi), ("dh", hi)])
             ops.gemm(dh, bw["f1w"], dln, b_mn_major=True)
+            gi, gb = take("gb")
             call("dig_layernorm_bwd", dln, a["xm"], a["mean2"], a["rstd2"], bw["n2w"], None, g, g, gb,
                  grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], grads[nm + "attn.proj.bias"], M, d, 0)
             # ---- attention (F:87-125) ----
-            ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             # output-projection dgrad; its epilogue also emits D = rowsum(dO o O) per (token, head) for the attention backward
             ops.gemm(gb, bw["pw"], dat, b_mn_major=True, epilogue=ops.EPI_ROWDOT, aux=a["att"], rowdot=dsum)
+
+            def proj_wgrad(gb=gb, a=a, nm=nm):
+                ops.gemm(gb, a["att"], grads[nm + "attn.proj.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
+            on_side(proj_wgrad, [("gb", gi)])
+            qi, dqkv = take("dqkv")
             ops.attention_bwd_d(a["qkv"], dat, a["lse"], dsum, dqkv, h, self.scale)
-            dqkvb = B.zeroed("bw.dqkvb%d" % l, (3 * d,), F32, "bwd")
-            call("dig_colsum", dqkv, 0, 3 * d, dqkvb, None, M, 3 * d)
-            grads[nm + "attn.q_bias"].copy_(dqkvb[:d])
-            grads[nm + "attn.v_bias"].copy_(dqkvb[2 * d:])
-            ops.gemm(dqkv, a["ln1"], grads[nm + "attn.qkv.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
+
+            def qkv_wgrads(dqkv=dqkv, a=a, nm=nm, l=l):
+                dqkvb = B.zeroed("bw.dqkvb%d" % l, (3 * d,), F32, "bwd")
+                call("dig_colsum", dqkv, 0, 3 * d, dqkvb, None, M, 3 * d)
+                grads[nm + "attn.q_bias"].copy_(dqkvb[:d])
+                grads[nm + "attn.v_bias"].copy_(dqkvb[2 * d:])
+                ops.gemm(dqkv, a["ln1"], grads[nm + "attn.qkv.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
+            on_side(qkv_wgrads, [("dqkv", qi)])
             ops.gemm(dqkv, bw["qkvw"], dln, b_mn_major=True)
             prev_b2 = grads[W["blocks"][l - 1]["name"] + "mlp.fc2.bias"] if l > 0 else None
+            gi, gb = take("gb")
             call("dig_layernorm_bwd", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], None, g, g, gb,
                  grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], prev_b2, M, d, 0)
+        if two:
+            cur.wait_stream(side)
         # ---- patch embed + mask token (F:190-196, V:95-99); pos_embed carries no gradient (V:99 detach) ----
         pre = W["pre"]
         gz = B.get("bw.gz", (M, d), BF16)
