@@ -269,16 +269,21 @@ def gpu_arm(a):
         ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         # DRAM traffic per launch of the same kernel family from the committed ncu pass (profiles/r1_step_metrics.json, written by
         # scripts/ncu_step_metrics.sh + summarize_step_metrics.py on a B200); algorithmic bytes are counted live from the shapes.
-        traffic, tensor_pct, src = None, None, None
+        traffic, tensor_pct, src, ncu_tf = None, None, None, None
         pj = os.path.join(ROOT, "profiles", "r1_step_metrics.json")
         if os.path.isfile(pj) and a.batch == 128 and a.model == MODEL:
-            fam = json.load(open(pj)).get("gemm_family", {})
+            prof = json.load(open(pj))
+            fam = prof.get("gemm_family", {})
             traffic, tensor_pct, src = fam.get("dram_bytes_per_launch"), fam.get("tensor_pipe_active_pct_time_weighted"), "profiles/r1_step_metrics.json"
+            if fam.get("share_of_step") and prof.get("total_kernel_ms"):
+                # the same FLOPs over the GEMM kernels' own durations in the committed ncu launch list (cold-cache, serialised): the
+                # event-bracketed figure above also contains ~10 us of event/launch latency per launch
+                ncu_tf = (flops / 2) / (fam["share_of_step"] * prof["total_kernel_ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 / gemm2_bf16_tcgen05 (all encoder/head GEMM launches of the step)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": src, "algorithmic_bytes_per_launch": gbytes / max(n, 1),
                 "hbm_frac_at_algorithmic_bytes": (gbytes / (gms * 1e-3) / 1e9) / hbm if gms > 0 else None,
-                "ncu_tensor_pipe_active_pct": tensor_pct, "peak_source": how + " (sustained cuBLAS bf16)",
+                "ncu_tensor_pipe_active_pct": tensor_pct, "ncu_kernel_time_tflops": ncu_tf, "peak_source": how + " (sustained cuBLAS bf16)",
                 "launches_timed": n, "avg_launch_ms": gms / max(n, 1), "gemm_share_of_step": (gms / 2) / ms}
         gf = GFLOP_PER_CROP.get(a.model)
         if gf:
