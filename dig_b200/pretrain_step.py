@@ -112,6 +112,7 @@ class PretrainStep:
         self._ptr_sig = self._signature()
         self._build_shadows()
         self.saved = None
+        self.forward_serial = 0
         self._n_masked = {}
         self._grad_flat = None
         # The momentum branch (EMA update + no-grad forward) and the online branch are independent until the InfoNCE logits: they run
@@ -514,7 +515,8 @@ class PretrainStep:
         vis = torch.empty(n_m, 48, dtype=F32, device=dev)
         ops.gemm(t3, S_["pix_decoder.4.weight"], vis, bias=self._named["pix_decoder.4.bias"])
 
-        self.saved = dict(enc=sv_enc, W=W, pp=(pp_layers, sv_pp), proj=(proj_layers, sv_proj), pred=(pred_layers, sv_pred),
+        self.forward_serial += 1
+        self.saved = dict(serial=self.forward_serial, enc=sv_enc, W=W, pp=(pp_layers, sv_pp), proj=(proj_layers, sv_proj), pred=(pred_layers, sv_pred),
                           qn=qn, qinv=qinv, k1_all=k1_all, k2_all=k2_all, lg1=lg1, lg2=lg2, Q=Q, Nk=Nk, C=C, Bsz=Bsz,
                           idx=idx, n_m=n_m, g0=g0, t1=t1, t2=t2, t3=t3, dmean=dmean, drstd=drstd, pooled=pooled)
         contra = res[:, 0].sum()
@@ -613,11 +615,17 @@ class _PretrainFn(torch.autograd.Function):
     def forward(ctx, step, image, aug_image, vis_mask_pos, m, only_mim, *params):
         contra, vis, accs = step.forward(image, aug_image, vis_mask_pos, m, only_mim)
         ctx.step = step
+        ctx.serial = step.forward_serial
         ctx.mark_non_differentiable(accs)
         return contra, vis, accs
 
     @staticmethod
     def backward(ctx, d_contra, d_vis, _d_accs):
+        sv = ctx.step.saved
+        if sv is None or sv.get("serial") != ctx.serial:
+            # activations live in per-model buffers that every forward overwrites: only the most recent forward can be back-propagated
+            raise ops.DigError("backward of a stale forward: dig_b200 keeps the activations of the most recent forward only "
+                               "(run backward before the next forward of the same model)")
         grads = ctx.step.backward(d_contra, d_vis)
         return (None, None, None, None, None, None) + tuple(grads)
 
