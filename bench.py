@@ -179,6 +179,9 @@ def gpu_arm(a):
     if world > 1:
         net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
         net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
+        if os.environ.get("DIG_BENCH_NOOP_ALLREDUCE") == "1":     # experiment only: how much of the step is DDP's gradient all-reduce?
+            from torch.distributed.algorithms.ddp_comm_hooks.debugging_hooks import noop_hook
+            net.register_comm_hook(None, noop_hook)
     decay, no_decay = [], []
     for n, p in model.named_parameters():
         if p.requires_grad:
