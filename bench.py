@@ -177,11 +177,18 @@ def gpu_arm(a):
     model.to(dev).train()
     net = model
     if world > 1:
-        net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
-        if os.environ.get("DIG_BENCH_NOOP_ALLREDUCE") == "1":     # experiment only: how much of the step is DDP's gradient all-reduce?
-            from torch.distributed.algorithms.ddp_comm_hooks.debugging_hooks import noop_hook
-            net.register_comm_hook(None, noop_hook)
+        # (DIG_BENCH_NO_SYNCBN=1, experiment only: per-rank BatchNorm statistics, to size the cost of the SyncBN collectives)
+        net = model if os.environ.get("DIG_BENCH_NO_SYNCBN") == "1" else torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        if os.environ.get("DIG_BENCH_DDP", "dig") == "torch":
+            # the reference runner's wrapper (R:391): works, but pays 2 x 183 per-parameter bucket copies and an unoverlapped all-reduce
+            net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local],
+                                                            find_unused_parameters=os.environ.get("DIG_BENCH_FIND_UNUSED", "1") != "0")
+            if os.environ.get("DIG_BENCH_NOOP_ALLREDUCE") == "1":     # experiment only: how much of the step is DDP's gradient all-reduce?
+                from torch.distributed.algorithms.ddp_comm_hooks.debugging_hooks import noop_hook
+                net.register_comm_hook(None, noop_hook)
+        else:
+            from dig_b200.parallel import DigDataParallel
+            net = DigDataParallel(net)     # flat-buffer gradient averaging overlapped with the backward (dig_b200/parallel.py)
     decay, no_decay = [], []
     for n, p in model.named_parameters():
         if p.requires_grad:
@@ -305,7 +312,7 @@ def gpu_arm(a):
                 "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "%s bs=%d/GPU num_view=2 mask_ratio=0.7 fwd+bwd+EMA+AdamW (BASELINE configs[%d])" % (
-                    a.model, B, 1 if world == 1 else 2), "global_batch": B * world, "parallelism": "dp%d" % world,
+                    a.model, B, 1 if world == 1 else 2), "global_batch": B * world, "parallelism": "dp%d" % world, "dp_wrapper": (os.environ.get("DIG_BENCH_DDP", "dig") if world > 1 else None),
                     "l2": "per-step working set (>10 GB of saved activations) far exceeds the 126 MB L2; no explicit flush"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "loss": loss_val}
         print(json.dumps(line))

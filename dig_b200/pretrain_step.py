@@ -182,6 +182,8 @@ class PretrainStep:
             goff[n] = total
             total += (self._named[n].numel() + 3) // 4 * 4
         self.grad_off, self.grad_total = goff, total
+        from .parallel import grad_segments
+        self.grad_seg = grad_segments(self.train_names, goff, total)     # heads / block l / embed -> [start, end) of the flat buffer
         self.momentum_warm = False
 
     def trainable_params(self):
@@ -349,6 +351,8 @@ class PretrainStep:
             gi, gb = take("gb")
             call("dig_layernorm_bwd", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], None, g, g, gb,
                  grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], prev_b2, M, d, 0)
+            # block l is final once this LayerNorm backward (chain) and its weight gradients (side stream) are done
+            self._allreduce_segment("block%d" % l, stream=side)
         if two:
             cur.wait_stream(side)
         # ---- patch embed + mask token (F:190-196, V:95-99); pos_embed carries no gradient (V:99 detach) ----
@@ -554,6 +558,11 @@ class PretrainStep:
             flat = self._grad_flat
             flat.zero_()
         grads = self._grad_views(flat)
+        sync = getattr(model, "_dig_grad_sync", None)
+        world, _ = _world()
+        self._sync_works = []
+        self._sync_flat = flat if (sync is not None and world > 1) else None
+        self._sync_group = sync.process_group if sync is not None else None
         Bf.zero_phase("bwd")
         g = Bf.get("bw.g", (M, d), F32)
         S_ = self.shadow
@@ -601,11 +610,32 @@ class PretrainStep:
             call("dig_scatter_add_rows", dg0, sv["idx"], g, n_m, d)
 
         # ---- encoder ----
+        self._allreduce_segment("heads")          # every head gradient is final: average it while the encoder backward runs
         gb = Bf.get("bw.gb", (M, d), BF16)
         call("dig_cast_f32_bf16", g, gb, M * d)
         self._encoder_bwd(sv["W"], sv["enc"], g, gb, grads)
+        self._allreduce_segment("embed")
+        for w in self._sync_works:                 # the current stream waits for the NCCL work (no host block)
+            w.wait()
+        self._sync_works = []
         self.saved = None
         return [grads[n] for n in self.train_names]
+
+    def _allreduce_segment(self, key, stream=None, after=None):
+        """DigDataParallel: average one finished segment of the flat gradient buffer over the ranks (async NCCL all-reduce, issued on
+        `stream` -- the side stream during the encoder backward -- after the event `after` recorded on the chain stream)."""
+        if self._sync_flat is None:
+            return
+        a, b = self.grad_seg[key]
+        cur = torch.cuda.current_stream()
+        st = cur if stream is None else stream
+        if st is not cur:
+            if after is None:
+                after = torch.cuda.Event()
+                after.record(cur)
+            st.wait_event(after)
+        with torch.cuda.stream(st):
+            self._sync_works.append(dist.all_reduce(self._sync_flat[a:b], op=dist.ReduceOp.AVG, group=self._sync_group, async_op=True))
 
 
 class _PretrainFn(torch.autograd.Function):

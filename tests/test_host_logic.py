@@ -89,6 +89,23 @@ def _worker_body(rank, world, port, q):
     m.update(float(rank + 1), n=1)
     m.synchronize_between_processes()
     ok = ok and m.global_avg == pytest.approx(sum(r + 1 for r in range(world)) / world)
+    # DigDataParallel (dig_b200/parallel.py): construction broadcasts rank 0's parameters and buffers; the handle it leaves on the
+    # wrapped module must not make the wrapper a child of its own child (train()/state_dict() would recurse)
+    import dig_b200
+    from dig_b200 import modeling  # noqa: F401
+    from dig_b200.parallel import DigDataParallel
+    torch.manual_seed(100 + rank)       # different initial weights per rank
+    net = dig_b200.create_model("pretrain_simmim_moco_ori_vit_tiny_patch4_32x128", pretrained=False, drop_path_rate=0.0,
+                                drop_block_rate=None, mlp_dim=64, dim=32, T=0.2, num_windows=4, encoder_type="vit", queue_size=8,
+                                patchnet_name="no_patchtrans")
+    wrapped = DigDataParallel(net)
+    wrapped.train()
+    chk = torch.stack([p.detach().double().sum() for p in net.parameters()]).sum().reshape(1)
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    ok = ok and all(torch.equal(b, both[0]) for b in both)
+    ok = ok and net.__dict__.get("_dig_grad_sync") is wrapped and all(k.startswith("module.") for k in wrapped.state_dict())
+    ok = ok and sum(1 for _ in wrapped.modules()) == 1 + sum(1 for _ in net.modules())
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
@@ -104,3 +121,25 @@ def test_two_rank_layout_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_grad_segments_cover_the_flat_buffer_in_backward_order():
+    """dig_b200.parallel.grad_segments: heads / 12 blocks / embed, contiguous, covering [0, total) (DigDataParallel all-reduces them)."""
+    import dig_b200
+    from dig_b200 import modeling  # noqa: F401
+    from dig_b200.parallel import grad_segments
+    m = dig_b200.create_model("pretrain_simmim_moco_ori_vit_tiny_patch4_32x128", pretrained=False, drop_path_rate=0.0, drop_block_rate=None,
+                              mlp_dim=256, dim=64, T=0.2, num_windows=4, encoder_type="vit", queue_size=8, patchnet_name="no_patchtrans")
+    names = [n for n, p in m.named_parameters() if p.requires_grad]
+    named = dict(m.named_parameters())
+    off, total = {}, 0
+    for n in names:
+        off[n] = total
+        total += (named[n].numel() + 3) // 4 * 4
+    seg = grad_segments(names, off, total)
+    assert set(seg) == {"heads", "embed"} | {"block%d" % i for i in range(12)}
+    spans = sorted(seg.values())
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert seg["embed"][0] == 0 and seg["heads"][1] == total
+    assert seg["block3"] == (off["encoder.blocks.3.norm1.weight"], off["encoder.blocks.4.norm1.weight"])
