@@ -1,4 +1,4 @@
-// dig_b200 -- loss-side kernels, all fp32 (the InfoNCE logits carry a 1/T = 5 gain, so they stay out of bf16):
+// dig_b200 -- loss-side kernels, fp32 (the InfoNCE logits carry a 1/T = 5 gain: they run on tcgen05 as a bf16 x 3 split GEMM):
 //   L2 row normalisation fwd/bwd (F.normalize, M:446-447), a small fp32 tiled GEMM for the q.k^T logits and their
 //   gradient (torch.einsum, M:451), the fused row-wise cross-entropy / top-k accuracy (M:453-461, M:593-625) and the
 //   masked-pixel MSE with on-the-fly target patchify (E:85-111, E:141).
@@ -31,6 +31,37 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
   s = warp_sum(s);
   const float k = inv_norm[row] * (gscale ? gscale[0] : 1.f);
   for (int c = lane; c < C; c += 32) dx[row * C + c] = (dy[row * C + c] - y[row * C + c] * s) * k;
+}
+
+// ---- bf16 x 3 operand split for the InfoNCE logits on tensor cores --------------------------------------
+// x = hi + lo + O(2^-17 |x|) with hi = bf16(x), lo = bf16(x - hi).  q.k = qh.kh + qh.kl + ql.kh + O(2^-16): ONE bf16 tcgen05 GEMM over
+// the 3x longer reduction axis [hi | hi | lo] . [hi | lo | hi] reproduces the fp32 logits (gain 1/T = 5, M:451) to ~1e-5 -- every bf16
+// product is exact in the fp32 TMEM accumulator.
+//   out_cat   [rows, 3*cols]            parts side by side (K-major operand); part `cat_lo_part` holds lo, the other two hi
+//   out_stack [rows/stack_rows, 3, stack_rows, cols]   planes (hi, lo, hi) per batch (MN-major B operand of the gradient GEMM)
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out_cat, int cat_lo_part, __nv_bfloat16* __restrict__ out_stack,
+                    long long stack_rows, long long rows, int cols) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one float4 per thread
+  const int c4n = cols >> 2;
+  if (i4 >= rows * c4n) return;
+  const long long r = i4 / c4n;
+  const int c = (int)(i4 % c4n) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * cols + c);
+  const uint2 hi = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  const uint2 lo = make_uint2(pack_bf16(v.x - bf16_lo(hi.x), v.y - bf16_hi(hi.x)), pack_bf16(v.z - bf16_lo(hi.y), v.w - bf16_hi(hi.y)));
+  if (out_cat != nullptr) {
+    __nv_bfloat16* o = out_cat + r * 3 * cols + c;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) *reinterpret_cast<uint2*>(o + (long long)j * cols) = (j == cat_lo_part) ? lo : hi;
+  }
+  if (out_stack != nullptr) {
+    const long long b = r / stack_rows, rr = r % stack_rows;
+    __nv_bfloat16* o = out_stack + ((b * 3) * stack_rows + rr) * cols + c;
+    *reinterpret_cast<uint2*>(o) = hi;
+    *reinterpret_cast<uint2*>(o + stack_rows * cols) = lo;
+    *reinterpret_cast<uint2*>(o + 2 * stack_rows * cols) = hi;
+  }
 }
 
 // ---- fp32 GEMM on CUDA cores: C[M,N] = alpha * A[M,K] . (B_NT ? B[N,K]^T : B[K,N]) ----------------------
@@ -131,23 +162,45 @@ infonce_rows_kernel(float* __restrict__ logits, int Q, int Nk, long long label_o
 
 // ---- masked-pixel MSE (E:85-111,141): target = un-normalised RGB patch '(p1 p2 c)' of view 0 at token row idx[r] -----
 // loss[0] += sum (pred - target)^2 / numel ; dpred = 2 (pred - target) / numel
+// One thread per (row, p1): the 12 consecutive prediction columns (p2, c) of one patch line = three 128-bit loads of pred, three 128-bit
+// loads of the image (the four p2 pixels of each colour plane are contiguous and 16-byte aligned), three 128-bit stores of dpred.
 __global__ void __launch_bounds__(256)
 masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ images, const int* __restrict__ idx, float* __restrict__ loss,
                   float* __restrict__ dpred, long long n_rows) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long numel = n_rows * 48;
+  const float inv_numel = 1.0f / (float)(n_rows * 48);
   float e = 0.f;
-  if (i < numel) {
-    const long long r = i / 48;
-    const int k = (int)(i % 48);
-    const int c = k % 3, p2 = (k / 3) & 3, p1 = k / 12;
+  if (i < n_rows * 4) {
+    const long long r = i >> 2;
+    const int p1 = (int)(i & 3);
     const int tok_row = idx[r];
     const long long b = tok_row >> 8;
     const int tok = tok_row & 255, ph = tok >> 5, pw = tok & 31;
-    const float tgt = images[((b * 3 + c) * 32 + ph * 4 + p1) * 128 + pw * 4 + p2] * 0.5f + 0.5f;
-    const float df = pred[i] - tgt;
-    e = df * df;
-    if (dpred) dpred[i] = 2.f * df / (float)numel;
+    float t[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(images + ((b * 3 + c) * 32 + ph * 4 + p1) * 128 + pw * 4));
+      t[c][0] = v.x * 0.5f + 0.5f; t[c][1] = v.y * 0.5f + 0.5f; t[c][2] = v.z * 0.5f + 0.5f; t[c][3] = v.w * 0.5f + 0.5f;
+    }
+    const float* pr = pred + r * 48 + p1 * 12;
+    float d[12];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(pr + 4 * q);
+      d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {     // column j of the line = (p2 = j / 3, c = j % 3)
+      d[j] -= t[j % 3][j / 3];
+      e += d[j] * d[j];
+    }
+    if (dpred) {
+      float* dp = dpred + r * 48 + p1 * 12;
+      const float k = 2.f * inv_numel;
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        *reinterpret_cast<float4*>(dp + 4 * q) = make_float4(d[4 * q] * k, d[4 * q + 1] * k, d[4 * q + 2] * k, d[4 * q + 3] * k);
+    }
   }
   e = warp_sum(e);
   __shared__ float red[8];
@@ -156,7 +209,7 @@ masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ imag
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(loss, t / (float)numel);
+    atomicAdd(loss, t * inv_numel);
   }
 }
 
@@ -181,6 +234,19 @@ extern "C" int dig_l2norm_bwd(const float* dy, const float* y, const float* inv_
                               int32_t C, void* stream) {
   DIG_REQUIRE(dy && y && inv_norm && dx && rows > 0 && C > 0, "dig_l2norm_bwd: bad arguments");
   l2norm_bwd_kernel<<<(int)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dy, y, inv_norm, gscale, dx, rows, C);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_split_bf16x3(const float* x, void* out_cat, int32_t cat_lo_part, void* out_stack, int64_t stack_rows, int64_t rows,
+                                int32_t cols, void* stream) {
+  DIG_REQUIRE(x && (out_cat || out_stack) && rows > 0 && cols > 0 && cols % 4 == 0, "dig_split_bf16x3: bad arguments (cols must be a multiple of 4)");
+  DIG_REQUIRE(cat_lo_part >= 0 && cat_lo_part < 3, "dig_split_bf16x3: cat_lo_part must be 0, 1 or 2");
+  DIG_REQUIRE(!out_stack || (stack_rows > 0 && rows % stack_rows == 0), "dig_split_bf16x3: rows must be a multiple of stack_rows");
+  DIG_REQUIRE(((((uintptr_t)x) & 15) | (((uintptr_t)out_cat) & 7) | (((uintptr_t)out_stack) & 7)) == 0, "dig_split_bf16x3: misaligned operand");
+  const long long n4 = rows * (cols >> 2);
+  split_bf16x3_kernel<<<(int)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_cat, cat_lo_part, (__nv_bfloat16*)out_stack,
+                                                                               stack_rows > 0 ? stack_rows : 1, rows, cols);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -210,8 +276,8 @@ extern "C" int dig_infonce_rows(float* logits, int32_t Q, int32_t Nk, int64_t la
 extern "C" int dig_masked_mse(const float* pred, const float* images, const int32_t* idx, float* loss, float* dpred, int64_t n_rows,
                               void* stream) {
   DIG_REQUIRE(pred && images && idx && loss && n_rows > 0, "dig_masked_mse: bad arguments");
-  const long long numel = n_rows * 48;
-  masked_mse_kernel<<<(int)((numel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, images, idx, loss, dpred, n_rows);
+  DIG_REQUIRE(((((uintptr_t)pred) | ((uintptr_t)images) | ((uintptr_t)dpred)) & 15) == 0, "dig_masked_mse: pred, images and dpred must be 16-byte aligned");
+  masked_mse_kernel<<<(int)((n_rows * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, images, idx, loss, dpred, n_rows);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -551,6 +551,9 @@ __global__ void mask_to_index_kernel(const uint8_t* __restrict__ mask, int* __re
     if (set && pos < n_per) idx[(long long)b * n_per + pos] = b * 256 + t0 + lane;
     base += __popc(bal);
   }
+  // a sample with too few set bits: the rest of its index slots still get a valid row (its first token), so that the gather / scatter /
+  // loss kernels downstream never see uninitialised indices; err tells the host, which raises
+  for (int pos = base + lane; pos < n_per; pos += 32) idx[(long long)b * n_per + pos] = b * 256;
   if (lane == 0 && base != n_per) atomicExch(err, 1);
 }
 

@@ -80,7 +80,7 @@ int num_sms() {
 
 }  // namespace dig
 
-extern "C" int dig_version(void) { return 1; }
+extern "C" int dig_version(void) { return 2; }
 
 extern "C" int dig_sm(void) {
   int dev = 0, major = 0, minor = 0;

@@ -2,7 +2,7 @@
 
 Reference semantics: `concat_all_gather` (modeling_pretrain_moco_mim_ori.py:580-591) concatenates the per-rank key
 blocks in rank order, and `contrastive_loss` labels row i of rank r with `i + N*r` (M:453).  dig_b200 gathers
-[k1 ; k2] of every rank with ONE all_gather_into_tensor and splits it here.
+[k1 ; k2] of every rank with ONE all_gather_into_tensor and regroups it here.
 """
 import torch
 import torch.distributed as dist
@@ -14,21 +14,22 @@ def world_and_rank():
     return 1, 0
 
 
-def gather_keys(kn, out_all=None):
-    """kn: [2Q, C] = normalised [k1 ; k2] of this rank.  Returns (k1_all [W*Q, C], k2_all [W*Q, C]) in rank order."""
+def gather_keys(kn, out_all=None, out2=None):
+    """kn: [2Q, C] = normalised [k1 ; k2] of this rank.  Returns k_all2 [2, W*Q, C] (contiguous): k_all2[0] = k1 of every rank in rank
+    order, k_all2[1] = k2 of every rank -- the row order `concat_all_gather` produces for each of the two calls (M:551-552)."""
     world, _ = world_and_rank()
     R, C = kn.shape
     Q = R // 2
     if world == 1:
-        return kn[:Q], kn[Q:]
+        return kn.view(2, Q, C)
     if out_all is None:
         out_all = torch.empty(world * R, C, dtype=kn.dtype, device=kn.device)
     out_all = out_all.view(world * R, C)
     dist.all_gather_into_tensor(out_all, kn.contiguous())
-    out_all = out_all.view(world, R, C)
-    k1_all = out_all[:, :Q].reshape(world * Q, C)
-    k2_all = out_all[:, Q:].reshape(world * Q, C)
-    return k1_all, k2_all
+    if out2 is None:
+        out2 = torch.empty(2, world * Q, C, dtype=kn.dtype, device=kn.device)
+    out2.view(2, world, Q, C).copy_(out_all.view(world, 2, Q, C).permute(1, 0, 2, 3))
+    return out2
 
 
 def label_offset(num_queries, rank):

@@ -5,7 +5,8 @@
     the un-normalised view-0 pixels on the fly;
   * the model call is one autograd node running the sm_100a kernels (no autocast: operands are bf16 by
     construction, statistics / losses fp32);
-  * the ~10 blocking `.item()` reads per step (E:123-176) are replaced by ONE packed device->host copy, consumed one step late.
+  * the ~10 blocking `.item()` reads per step (E:123-176) are replaced by ONE packed device->host copy, consumed one step late;
+    a non-finite loss still never reaches the weights: the optimizer launch is guarded by the loss value on the device.
 """
 import math
 import sys
@@ -45,8 +46,10 @@ def masked_pixel_mse(pred, images, mask_view0):
         raise ops.DigError("masked_pixel_mse runs on CUDA tensors only")
     idx = torch.empty(B * n, dtype=torch.int32, device=pred.device)
     err = torch.zeros(1, dtype=torch.int32, device=pred.device)
-    call("dig_mask_to_index", mask_view0.to(torch.uint8).contiguous(), idx, err, B, n)
-    return _MaskedPixelMSE.apply(pred, images.contiguous(), idx)
+    call("dig_mask_to_index", mask_view0.to(torch.uint8).contiguous(), idx, err, B, n)      # always writes B*n in-bounds indices
+    loss = _MaskedPixelMSE.apply(pred, images.contiguous(), idx)
+    loss._dig_mask_err = err      # device flag: some sample did not have exactly n masked patches (train_one_epoch reads it back)
+    return loss
 
 
 def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader, word_data_loader, optimizer, device, epoch,
@@ -81,7 +84,7 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
     else:
         w = np.zeros(n_it)
 
-    pinned = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pinned = [torch.empty(9, dtype=torch.float32).pin_memory() for _ in range(2)]
     pending = None
 
     def consume(rec):
@@ -90,8 +93,12 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
         packed = slot.tolist()
         loss_value = packed[0]
         if not math.isfinite(loss_value):                                                             # E:148-150
+            # The check runs one step late, but the non-finite step changed nothing: FusedAdamW's launch is guarded by the loss on the
+            # device (dig_mt_adamw `guard`), so weights, moments and every checkpoint written before this point are clean.
             print("Loss is {}, stopping training".format(loss_value))
             sys.exit(1)
+        if packed[8] != 0.0:
+            raise ops.DigError("a batch did not mask the same number of patches in every sample (masking_generator.py:20)")
         metric_logger.update(loss_contrast=packed[1], q1_acc1=packed[3], q1_acc5=packed[4], q2_acc1=packed[5], q2_acc5=packed[6],
                              loss_pixel=packed[2], loss=loss_value, loss_scale=loss_scale_value)
         metric_logger.update(lr=lr_max, min_lr=lr_min, weight_decay=wd, grad_norm=packed[7])
@@ -136,7 +143,8 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
         # host never drains the GPU queue inside the epoch.  Values, averages and the returned dict are unchanged; log lines lag a step.
         packed = torch.stack([loss.detach().float().reshape(()), contra.detach().float().reshape(()), loss_pixel.detach().reshape(()),
                               out["q1_acc1"].reshape(()), out["q1_acc5"].reshape(()), out["q2_acc1"].reshape(()),
-                              out["q2_acc5"].reshape(()), grad_norm.to(loss.device).float().reshape(())])
+                              out["q2_acc5"].reshape(()), grad_norm.to(loss.device).float().reshape(()),
+                              loss_pixel._dig_mask_err.float().reshape(())])
         slot = pinned[step & 1]
         slot.copy_(packed, non_blocking=True)
         ev = torch.cuda.Event()
@@ -154,6 +162,9 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
             lr_scheduler.step_update(start_steps + step)
         if step >= 1 and step % (args.eval_freq * 10) == 0 and getattr(args, "output_dir", None):
             from .checkpoint import save_model
+            if pending is not None:        # never write a checkpoint of a step whose loss has not passed the finite check (E:148-150)
+                consume(pending)
+                pending = None
             save_model(args=args, model=model, model_without_ddp=getattr(model, "module", model), optimizer=optimizer,
                        loss_scaler=loss_scaler, epoch="{0}_{1}".format(epoch, step))
         sys.stdout.flush()

@@ -153,6 +153,12 @@ class DigMoCoViT(nn.Module):
             raise NotImplementedError("drop_path must be 0.0 on the pre-training path (R:87)")
         if not qkv_bias or label_smoothing != 0.0 or not use_pix_projector:
             raise NotImplementedError("only qkv_bias=True, label_smoothing=0, use_pix_projector=True are built")
+        if encoder_embed_dim != 64 * encoder_num_heads:
+            raise NotImplementedError("the attention kernels are built for head_dim 64 (got d=%d, heads=%d)" % (encoder_embed_dim, encoder_num_heads))
+        grid_w = img_size[1] // patch_size
+        if num_windows <= 0 or grid_w % num_windows != 0:
+            raise NotImplementedError("num_windows must divide the %d patch columns (README.md:76 runs --num_windows 4); got %r -- "
+                                      "adaptive_avg_pool2d's uneven windows (M:192) are not built" % (grid_w, num_windows))
         self.T = T
         self.num_windows = num_windows
         self.use_pixel_target = True
@@ -207,6 +213,9 @@ class DigMoCoViT(nn.Module):
         """Same contract as M:488-577: returns {'contra_loss', 'q{1,2}_acc{1,5}', 'vis_out': [ [B,n,48] ]}."""
         if not image.is_cuda:
             raise RuntimeError("dig_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
+        if not self.training:
+            raise NotImplementedError("eval mode is not built: the BatchNorm heads always normalise with batch statistics and update their "
+                                      "running estimates (the pre-training runner never leaves train mode, E:35)")
         from .pretrain_step import run_model
         return run_model(self._pipeline(), image, aug_image, vis_mask_pos, float(m), bool(only_mim_on_ori_img))
 

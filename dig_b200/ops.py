@@ -89,6 +89,35 @@ def load():
     return lib
 
 
+# bf16 GEMM-operand shadows of fp32 master parameters, keyed by the parameter's data_ptr(): PretrainStep registers them, FusedAdamW looks
+# them up so that its single launch also refreshes them (no separate fp32 -> bf16 cast pass per step).
+import weakref
+
+_shadows = weakref.WeakValueDictionary()      # entries vanish with the PretrainStep that owns the shadow tensors
+
+
+def register_shadow(param, shadow):
+    _shadows[param.data_ptr()] = shadow
+
+
+def shadow_of(param):
+    return _shadows.get(param.data_ptr())
+
+
+_raw_writes = 0
+
+
+def note_raw_parameter_write():
+    """Call after writing parameters behind autograd's back (through `.data` or a raw pointer) WITHOUT refreshing their registered
+    shadows: the next forward re-casts them.  (In-place torch ops on the parameters bump `Tensor._version`, which is watched too.)"""
+    global _raw_writes
+    _raw_writes += 1
+
+
+def raw_parameter_writes():
+    return _raw_writes
+
+
 _launches = 0
 _gemm_prof = None   # None, or a list of (event0, event1, flops) while profiling
 
@@ -214,6 +243,33 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
     return out
 
 
+_attn_prof = None   # None, or {"fwd": [(e0, e1, flops, exps)], "bwd": [...]} while profiling
+
+
+def profile_attention(enable):
+    """Per-launch CUDA-event timing of the fused attention kernels.  profile_attention(False) -> {"fwd"/"bwd": (flops, ms, launches,
+    exp2 count)} -- algorithmic FLOPs 4*256*256*64 (forward) / 10*256*256*64 (backward) per (sequence, head), no recompute counted."""
+    global _attn_prof
+    if enable:
+        _attn_prof = {"fwd": [], "bwd": []}
+        return None
+    torch.cuda.synchronize()
+    rec, _attn_prof = _attn_prof or {"fwd": [], "bwd": []}, None
+    return {k: (sum(r[2] for r in v), sum(r[0].elapsed_time(r[1]) for r in v), len(v), sum(r[3] for r in v)) for k, v in rec.items()}
+
+
+def _attn_timed(kind, items, fn):
+    if _attn_prof is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    per = 256 * 256 * 64
+    _attn_prof[kind].append((e0, e1, float(items) * per * (4 if kind == "fwd" else 10), float(items) * 256 * 256 * (1 if kind == "fwd" else 1)))
+    return r
+
+
 def attention_fwd(qkv, out, lse, heads, scale, p_in_smem=False):
     """Fused softmax(q k^T * scale) v over 256-token sequences (F:97-118). qkv bf16 [S*256, 3*heads*64]."""
     _req(qkv, torch.bfloat16, "qkv"); _req(out, torch.bfloat16, "out")
@@ -225,8 +281,8 @@ def attention_fwd(qkv, out, lse, heads, scale, p_in_smem=False):
         _req(lse, torch.float32, "lse")
         if lse.numel() != rows // 256 * heads * 256:
             raise DigError("attention_fwd: lse must hold [S, heads, 256]")
-    _check(load().dig_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), rows // 256, heads, scale, int(p_in_smem), _stream()),
-           "dig_attention_fwd")
+    _attn_timed("fwd", rows // 256 * heads, lambda: _check(load().dig_attention_fwd(
+        _ptr(qkv), _ptr(out), _ptr(lse), rows // 256, heads, scale, int(p_in_smem), _stream()), "dig_attention_fwd"))
     count_launch()
     return out
 
@@ -261,7 +317,7 @@ def attention_bwd_d(qkv, dout, lse, dsum, dqkv, heads, scale):
     if qkv.shape != dqkv.shape or qkv.shape[1] != 3 * d or tuple(dout.shape) != (rows, d) or rows % 256 or \
             tuple(dsum.shape) != (rows, heads) or not dsum.is_contiguous():
         raise DigError("attention_bwd_d: bad shapes")
-    _check(load().dig_attention_bwd_d(_ptr(qkv), _ptr(dout), _ptr(lse), _ptr(dsum), _ptr(dqkv), rows // 256, heads, scale, _stream()),
-           "dig_attention_bwd_d")
+    _attn_timed("bwd", rows // 256 * heads, lambda: _check(load().dig_attention_bwd_d(
+        _ptr(qkv), _ptr(dout), _ptr(lse), _ptr(dsum), _ptr(dqkv), rows // 256, heads, scale, _stream()), "dig_attention_bwd_d"))
     count_launch()
     return dqkv

@@ -25,6 +25,8 @@ class DigDataParallel(torch.nn.Module):
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=0, group=process_group)
+        from . import ops
+        ops.note_raw_parameter_write()      # written through .data: the bf16 operand shadows must be re-cast
         # PretrainStep.backward looks this handle up and averages its flat gradient buffer segment by segment.  It goes into the instance
         # __dict__ directly: a plain attribute assignment would register the wrapper as a child module of its own child (a cycle).
         module.__dict__["_dig_grad_sync"] = self

@@ -103,6 +103,9 @@ class PretrainStep:
         if self.d != self.heads * 64:
             raise ops.DigError("head_dim must be 64 (d=%d heads=%d)" % (self.d, self.heads))
         self.depth = len(enc.blocks)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm) and mod.track_running_stats and mod.momentum is None:
+                raise ops.DigError("BatchNorm momentum=None (cumulative moving average) is not built; the reference uses the default 0.1 (M:463-482)")
         self.T = float(model.T)
         self.num_windows = int(model.num_windows)
         self.scale = 64 ** -0.5
@@ -114,11 +117,13 @@ class PretrainStep:
         self.saved = None
         self.forward_serial = 0
         self._n_masked = {}
+        self._mask_err = None      # (event, pinned int32[1]) of the previous forward's dig_mask_to_index error flag
         self._grad_flat = None
         # The momentum branch (EMA update + no-grad forward) and the online branch are independent until the InfoNCE logits: they run
         # on two streams so that one branch's HBM-bound kernels (LayerNorm, BatchNorm, casts) fill in under the other's GEMMs.
         import os
         self._two_streams = os.environ.get("DIG_TWO_STREAMS", "1") != "0"
+        self._always_cast = os.environ.get("DIG_ALWAYS_CAST", "0") == "1"
         self._side = torch.cuda.Stream(device=self.device) if self._two_streams else None
 
     # ------------------------------------------------------------------ parameter bookkeeping
@@ -156,6 +161,10 @@ class PretrainStep:
             self.shadow[n] = flat[offs[n]:offs[n] + p.numel()].view(shape)
         self.shadow_flat = flat
         self.tab_cast_online = MtTable(self.device, [self._named[n].data for n in on], [self.shadow[n] for n in on])
+        for n in on:
+            ops.register_shadow(self._named[n], self.shadow[n])     # FusedAdamW refreshes these in its own launch
+        self._online_gemm_params = [self._named[n] for n in on]
+        self._cast_state = None
         self.tab_cast_momentum = MtTable(self.device, [self._named[n].data for n in mo], [self.shadow[n] for n in mo])
         # EMA pairs: every parameter of encoder / projector / pix_projector (M:428-442)
         pairs = []
@@ -390,8 +399,7 @@ class PretrainStep:
             gamma, beta = (bn.weight, bn.bias) if bn.affine else (None, None)
             call("dig_bn_apply", z, stats, count, gamma, beta, 0 if last else 1, bn.eps, a_out, out_f32, rows, C)
             if bn.track_running_stats and bn.running_mean is not None:
-                mom = 0.1 if bn.momentum is None else bn.momentum
-                call("dig_bn_running", stats, count, mom, bn.running_mean, bn.running_var, bn.num_batches_tracked, C)
+                call("dig_bn_running", stats, count, bn.momentum, bn.running_mean, bn.running_var, bn.num_batches_tracked, C)
             saved.append(dict(a_in=a, z=z, stats=stats, count=count, a_out=a_out))
             a = a_out
         return out_f32, a, saved
@@ -435,6 +443,7 @@ class PretrainStep:
             raise ops.DigError("only_mim_on_ori_img=False is not built (README.md:75 runs with --only_mim_on_ori_img 1)")
         if vis_mask_pos.shape[1] != 2:
             raise ops.DigError("num_view must be 2 (README.md:66), got %d" % vis_mask_pos.shape[1])
+        self._check_mask_err()
         images = Bf.get("images", (S, 3, 32, 128), F32)
         images[:Bsz].copy_(image)
         images[Bsz:].copy_(aug_image)
@@ -442,9 +451,21 @@ class PretrainStep:
         mask_u8.view(2, Bsz, TOK).copy_(vis_mask_pos.permute(1, 0, 2))      # M:496-497 view-major
 
         Bf.zero_phase("fwd")
+        # masked rows of view 0 as an index list (M:569); done first so that its error flag is back on the host early (see _post_mask_err)
+        n_per = self._masked_per_sample(vis_mask_pos)
+        n_m = Bsz * n_per
+        idx = Bf.get("dec.idx", (max(n_m, 1),), torch.int32)
+        err = Bf.zeroed("dec.err", (1,), torch.int32, "fwd")
+        call("dig_mask_to_index", mask_u8, idx, err, Bsz, n_per)
+        self._post_mask_err(err)
         # bf16 shadows of the online weights + fused qkv bias
         cur = torch.cuda.current_stream()
-        self._mt("dig_mt_cast_bf16", self.tab_cast_online)
+        # bf16 shadows of the online GEMM weights: FusedAdamW rewrites them together with the fp32 masters, so the cast pass only runs
+        # when something else touched the parameters (first step, load_state_dict, another optimizer: in-place torch ops bump _version)
+        state = (sum(p._version for p in self._online_gemm_params), ops.raw_parameter_writes())
+        if state != self._cast_state or self._always_cast:
+            self._mt("dig_mt_cast_bf16", self.tab_cast_online)
+            self._cast_state = state
         self._mt("dig_mt_copy_f32", self.tab_qkv_bias["encoder."])
         side = self._side if self._two_streams else cur
         if side is not cur:
@@ -468,7 +489,13 @@ class PretrainStep:
             Q, C = R // 2, k.shape[1]
             kn = Bf.get("kn", (R, C), F32)
             call("dig_l2norm_fwd", k, kn, None, R, C)
-            k1_all, k2_all = dist_layout.gather_keys(kn, Bf.get("kall", (world, R, C), F32) if world > 1 else None)  # M:580-591
+            k_all2 = dist_layout.gather_keys(kn, Bf.get("kall", (world, R, C), F32) if world > 1 else None,
+                                             Bf.get("kall2", (2, world * Q, C), F32) if world > 1 else None)       # M:580-591
+            # operands of the logits GEMM (K-major [hi|lo|hi]) and of its gradient GEMM (MN-major planes), see dig_split_bf16x3
+            Nk = world * Q
+            k3 = Bf.get("nce.k3", (2, Nk, 3 * C), BF16)
+            k3s = Bf.get("nce.k3s", (2, 3 * Nk, C), BF16) if need_grad else None
+            call("dig_split_bf16x3", k_all2, k3, 1, k3s, Nk, 2 * Nk, C)
 
         # ---- online branch ----
         W = self._enc_weights("encoder.")
@@ -490,21 +517,17 @@ class PretrainStep:
         # ---- contrastive loss (M:444-461): q1.k2 + q2.k1 ----
         if side is not cur:
             cur.wait_stream(side)       # the keys (and the momentum weights the next EMA overwrites) are ready
-        Nk = world * Q
+        # logits on tcgen05: [qh|qh|ql] . [kh|kl|kh]^T over K = 3C reproduces the fp32 einsum of M:451 to ~1e-5 (q1.k2 and q2.k1)
         res = Bf.zeroed("nce.res", (2, 4), F32, "fwd")
-        lg1 = Bf.get("nce.lg1", (Q, Nk), F32)
-        lg2 = Bf.get("nce.lg2", (Q, Nk), F32)
-        call("dig_sgemm_f32", qn[:Q], k2_all, lg1, Q, Nk, C, 1, 1.0 / self.T)
-        call("dig_sgemm_f32", qn[Q:], k1_all, lg2, Q, Nk, C, 1, 1.0 / self.T)
-        call("dig_infonce_rows", lg1, Q, Nk, dist_layout.label_offset(Q, rank), self.T, res[0])
-        call("dig_infonce_rows", lg2, Q, Nk, dist_layout.label_offset(Q, rank), self.T, res[1])
+        q3 = Bf.get("nce.q3", (R, 3 * C), BF16)
+        call("dig_split_bf16x3", qn, q3, 2, None, 0, R, C)
+        lg = Bf.get("nce.lg", (2, Q, Nk), F32)
+        ops.gemm(q3[:Q], k3[1], lg[0], alpha=1.0 / self.T)
+        ops.gemm(q3[Q:], k3[0], lg[1], alpha=1.0 / self.T)
+        call("dig_infonce_rows", lg[0], Q, Nk, dist_layout.label_offset(Q, rank), self.T, res[0])
+        call("dig_infonce_rows", lg[1], Q, Nk, dist_layout.label_offset(Q, rank), self.T, res[1])
 
         # ---- masked-pixel decoder on the masked rows of view 0 (M:561-570; row-wise, so gather first) ----
-        n_per = self._masked_per_sample(vis_mask_pos)
-        n_m = Bsz * n_per
-        idx = Bf.get("dec.idx", (max(n_m, 1),), torch.int32)
-        err = Bf.zeroed("dec.err", (1,), torch.int32, "fwd")
-        call("dig_mask_to_index", mask_u8, idx, err, Bsz, n_per)
         g0 = Bf.get("dec.g0", (n_m, d), BF16)
         call("dig_gather_rows", enc, idx, g0, n_m, d)
         S_ = self.shadow
@@ -521,14 +544,32 @@ class PretrainStep:
 
         self.forward_serial += 1
         self.saved = dict(serial=self.forward_serial, enc=sv_enc, W=W, pp=(pp_layers, sv_pp), proj=(proj_layers, sv_proj), pred=(pred_layers, sv_pred),
-                          qn=qn, qinv=qinv, k1_all=k1_all, k2_all=k2_all, lg1=lg1, lg2=lg2, Q=Q, Nk=Nk, C=C, Bsz=Bsz,
+                          qn=qn, qinv=qinv, k3s=k3s, lg=lg, Q=Q, Nk=Nk, C=C, Bsz=Bsz,
                           idx=idx, n_m=n_m, g0=g0, t1=t1, t2=t2, t3=t3, dmean=dmean, drstd=drstd, pooled=pooled)
         contra = res[:, 0].sum()
         accs = res[:, 1:3].clone()      # [[q1_acc1, q1_acc5], [q2_acc1, q2_acc5]]
         return contra, vis.view(Bsz, n_per, 48), accs
 
+    def _post_mask_err(self, err):
+        """The number of masked patches per sample is validated on the host for the first batch of a shape only (a blocking read); every
+        later batch is validated by dig_mask_to_index on the device.  Its flag comes back through a pinned slot and is checked when the
+        NEXT forward starts (no host block inside the step): a ragged mask raises one step late, and never indexes out of bounds."""
+        if self._mask_err is None:
+            self._mask_err = [None, torch.zeros(1, dtype=torch.int32).pin_memory()]
+        self._mask_err[1].copy_(err, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._mask_err[0] = ev
+
+    def _check_mask_err(self):
+        if self._mask_err is not None and self._mask_err[0] is not None:
+            self._mask_err[0].synchronize()
+            self._mask_err[0] = None
+            if int(self._mask_err[1][0]) != 0:
+                raise ops.DigError("the previous batch did not mask the same number of patches in every sample (masking_generator.py:20)")
+
     def _masked_per_sample(self, vis_mask_pos):
-        key = (tuple(vis_mask_pos.shape), vis_mask_pos.data_ptr() if False else 0)
+        key = tuple(vis_mask_pos.shape)
         if key not in self._n_masked:
             cnt = vis_mask_pos[:, 0].sum(dim=1)
             n = int(cnt[0].item())
@@ -571,9 +612,12 @@ class PretrainStep:
         if d_contra is not None:
             Q, Nk, C = sv["Q"], sv["Nk"], sv["C"]
             R = 2 * Q
-            dqn = Bf.get("bw.dqn", (R, C), F32)
-            call("dig_sgemm_f32", sv["lg1"], sv["k2_all"], dqn[:Q], Q, C, Nk, 0, 1.0)
-            call("dig_sgemm_f32", sv["lg2"], sv["k1_all"], dqn[Q:], Q, C, Nk, 0, 1.0)
+            # d qn = dlogits . k_all on tcgen05 with the same three-term split (dlogits [hi|hi|lo] over K = 3 Nk, keys as MN-major planes)
+            dl3 = Bf.get("bw.dl3", (2 * Q, 3 * Nk), BF16)
+            call("dig_split_bf16x3", sv["lg"], dl3, 2, None, 0, 2 * Q, Nk)
+            dqn = Bf.zeroed("bw.dqn", (R, C), F32, "bwd")
+            ops.gemm(dl3[:Q], sv["k3s"][1], dqn[:Q], b_mn_major=True, split_k=-1)
+            ops.gemm(dl3[Q:], sv["k3s"][0], dqn[Q:], b_mn_major=True, split_k=-1)
             dq = Bf.get("bw.dq", (R, C), F32)
             gs = d_contra.reshape(1).to(F32).contiguous()
             call("dig_l2norm_bwd", dqn, sv["qn"], sv["qinv"], gs, dq, R, C)

@@ -37,7 +37,7 @@ class SmoothedValue(object):
         self.deque = deque(maxlen=window_size)
         self.total = 0.0
         self.count = 0
-        self.fmt = fmt or "{median:.4f} ({global_avg:.4f})"
+        self.fmt = fmt or "{avg:.4f} ({global_avg:.4f})"
 
     def update(self, value, n=1):
         self.deque.append(value)
@@ -195,6 +195,7 @@ class NativeScalerWithGradNormCount:
     def __init__(self):
         self._scale = 1.0
         self._gn = GradNorm()
+        self._sumsq_out = None
 
     def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
         loss.backward(create_graph=create_graph)
@@ -202,15 +203,34 @@ class NativeScalerWithGradNormCount:
             return None
         assert parameters is not None
         params = [p for p in parameters]
-        sumsq = self._gn.sumsq(params)
-        norm = torch.tensor(0.0) if sumsq is None else sumsq.sqrt().reshape(())
-        if clip_grad is not None and clip_grad > 0:
-            if hasattr(optimizer, "set_grad_transform"):
-                optimizer.set_grad_transform(1.0, sumsq, clip_grad)      # clipping folded into the AdamW launch
+        fused = hasattr(optimizer, "set_grad_transform")
+        if clip_grad is not None:
+            # U:487-490: `clip_grad is not None` clips -- also to 0.0, which zeroes every gradient (the engine's default max_norm=0)
+            sumsq = self._gn.sumsq(params)
+            norm = torch.tensor(0.0) if sumsq is None else sumsq.sqrt().reshape(())
+            if fused:
+                optimizer.set_grad_transform(1.0, sumsq, clip_grad, None, self._guard(loss))      # clipping folded into the AdamW launch
             else:
                 torch.nn.utils.clip_grad_norm_(params, clip_grad)
-        optimizer.step()
+            optimizer.step()
+        elif fused and any(p.grad is not None for p in params):
+            # U:492-493 get_grad_norm_: the AdamW launch sums the squared gradients it reads anyway (no second pass over them)
+            if self._sumsq_out is None or self._sumsq_out.device != loss.device:
+                self._sumsq_out = torch.zeros(1, dtype=torch.float32, device=loss.device)
+            self._sumsq_out.zero_()
+            optimizer.set_grad_transform(1.0, None, None, self._sumsq_out, self._guard(loss))
+            optimizer.step()
+            norm = self._sumsq_out.sqrt().reshape(())
+        else:
+            sumsq = self._gn.sumsq(params)
+            norm = torch.tensor(0.0) if sumsq is None else sumsq.sqrt().reshape(())
+            optimizer.step()
         return norm
+
+    @staticmethod
+    def _guard(loss):
+        g = loss.detach()
+        return g.reshape(1) if (g.is_cuda and g.dtype == torch.float32 and g.numel() == 1) else None
 
     def state_dict(self):
         return {"scale": self._scale}

@@ -127,6 +127,14 @@ int dig_mask_to_index(const uint8_t* mask, int32_t* idx, int32_t* err, int32_t B
 int dig_l2norm_fwd(const float* x, float* y, float* inv_norm, int64_t rows, int32_t C, void* stream);
 int dig_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, const float* gscale, float* dx, int64_t rows,
                    int32_t C, void* stream);
+/* Operand split for the InfoNCE logits / gradient on tcgen05 (M:451 torch.einsum('nc,mc->nm')): x fp32 [rows, cols] ->
+ * hi = bf16(x), lo = bf16(x - hi).  out_cat bf16 [rows, 3*cols] holds the three parts side by side with lo in part
+ * `cat_lo_part` (queries: [hi|hi|lo], lo part 2; keys: [hi|lo|hi], lo part 1), so that dig_gemm over K = 3*cols gives
+ * qh.kh + qh.kl + ql.kh = q.k to ~2^-16 relative.  out_stack bf16 [rows/stack_rows, 3, stack_rows, cols] holds the planes
+ * (hi, lo, hi) per batch of stack_rows rows: the MN-major B operand of the gradient GEMM.  Either output may be NULL.     */
+int dig_split_bf16x3(const float* x, void* out_cat, int32_t cat_lo_part, void* out_stack, int64_t stack_rows, int64_t rows,
+                     int32_t cols, void* stream);
+/* fp32 CUDA-core GEMM (kept as the in-library reference of the split path; off the step since ABI v2).  Was: InfoNCE logits */
 /* fp32 GEMM for the InfoNCE logits einsum('nc,mc->nm') (M:451) and its gradient: C = alpha * A[M,K] . B, with B given
  * as [N,K] (b_is_nk) or [K,N].                                                                        */
 int dig_sgemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N, int32_t K, int32_t b_is_nk, float alpha,
@@ -153,11 +161,16 @@ int dig_mt_ema(const int64_t* online, const int64_t* target, const int64_t* shad
 int dig_mt_sumsq(const int64_t* src, const int64_t* numel, const int32_t* blk_tensor, const int32_t* blk_chunk,
                  int32_t num_blocks, float* out, void* stream);
 /* AdamW (custom_optim/_functional.py:115-140) with per-tensor lr / weight_decay, gradient unscale (grad_scale) and
- * optional clip_grad_norm_ (max_norm > 0, sumsq[0] = squared norm of the scaled grads); refreshes the bf16 shadow. */
+ * optional clip_grad_norm_ (max_norm >= 0, negative = off; sumsq[0] = squared norm of the unscaled grads); refreshes the bf16 shadows
+ * (GEMM operands) of the tensors that have one; sumsq_out (may be NULL) += squared norm of the scaled gradients as read
+ * by this launch -- get_grad_norm_ (U:507-519) without a second pass when nothing is clipped; guard (may be NULL) is a
+ * device scalar (the step's loss): when it is not finite the launch changes nothing (the reference exits before the
+ * update, E:148-150).                                                                                             */
 int dig_mt_adamw(const int64_t* params, const int64_t* grads, const int64_t* exp_avg, const int64_t* exp_avg_sq,
                  const int64_t* shadow, const int64_t* numel, const float* lr, const float* weight_decay,
                  const int32_t* blk_tensor, const int32_t* blk_chunk, int32_t num_blocks, float beta1, float beta2,
-                 float eps, int64_t step, float grad_scale, const float* sumsq, float max_norm, void* stream);
+                 float eps, int64_t step, float grad_scale, const float* sumsq, float max_norm, float* sumsq_out,
+                 const float* guard, void* stream);
 
 #ifdef __cplusplus
 }
