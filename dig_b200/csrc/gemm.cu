@@ -228,7 +228,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
 
   GemmEpilogue ep;
   ep.out = g->out; ep.ldo = g->ldo;
-  ep.bias = g->bias; ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
+  ep.bias = g->bias ? g->bias : (MODE == DIG_EPI_GELU ? zero_bias() : nullptr); ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
   ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.colsum = g->colsum;
@@ -286,6 +286,16 @@ static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
   return -1;
 }
 
+__device__ float g_zero_bias[kZeroBiasLen];   // zero-initialised
+const float* zero_bias() {
+  static const float* p = nullptr;
+  if (p == nullptr) {
+    void* a = nullptr;
+    if (cudaGetSymbolAddress(&a, g_zero_bias) == cudaSuccess) p = reinterpret_cast<const float*>(a);
+  }
+  return p;
+}
+
 int gemm2_try(const dig_gemm_t* g, cudaStream_t s);  // gemm2.cu: 2-CTA kernel; returns 1 when it does not take the problem
 
 static bool use_2cta() {
@@ -316,6 +326,8 @@ extern "C" int dig_gemm(const dig_gemm_t* g_in, void* stream) {
   if (g->split_k > 1 || g->split_k < 0)
     DIG_REQUIRE(g->out_fp32 && g->epilogue == DIG_EPI_LINEAR && !g->bias && !g->residual && !g->row_mask && !g->colsum,
                 "dig_gemm: split_k needs a plain fp32 accumulate epilogue");
+  if (g->epilogue == DIG_EPI_GELU && g->bias == nullptr)
+    DIG_REQUIRE(g->N <= kZeroBiasLen, "dig_gemm: DIG_EPI_GELU without a bias supports N <= %d", kZeroBiasLen);
   if (g->epilogue == DIG_EPI_ROWDOT)
     DIG_REQUIRE(g->rowdot != nullptr && g->ldrowdot * 64 >= g->N && g->N % 64 == 0 && !g->out_fp32 && g->split_k == 1,
                 "dig_gemm: DIG_EPI_ROWDOT needs bf16 out, N %% 64 == 0 and rowdot[M, >= N/64]");

@@ -321,7 +321,7 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
 
   GemmEpilogue ep;
   ep.out = g->out; ep.ldo = g->ldo;
-  ep.bias = g->bias; ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
+  ep.bias = g->bias ? g->bias : (MODE == DIG_EPI_GELU ? zero_bias() : nullptr); ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
   ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.colsum = g->colsum;

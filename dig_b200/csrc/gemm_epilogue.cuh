@@ -34,6 +34,10 @@ struct GemmEpilogue {
   int dbg;  // bring-up only (env DIG_GEMM_DBG): 1 = skip the global stores, 2 = skip the whole epilogue body
 };
 
+// A device-resident zero vector standing in for a missing bias in the GELU epilogue (so that the bias add is unconditional there).
+const float* zero_bias();
+static constexpr int kZeroBiasLen = 8192;
+
 __device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
   const uint2 v = *reinterpret_cast<const uint2*>(p);
   return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));

@@ -12,6 +12,9 @@
 
 #include "gemm_epilogue.cuh"
 
+#ifndef DIG_EPI_EARLY_LD
+#define DIG_EPI_EARLY_LD 1  // 0: request an epilogue operand tile only one column group ahead (round-1 behaviour, A/B switch)
+#endif
 #ifndef DIG_GELU_PACKED
 #define DIG_GELU_PACKED 1   // 0: scalar FFMA GELU in the epilogues (A/B switch)
 #endif
@@ -45,6 +48,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
   constexpr int NGT = (BNT + G - 1) / G;          // column groups in the tile
   static_assert(BNT % G == 0, "tile width must be a multiple of the staging group");
   const bool has_ld = (MODE == DIG_EPI_GELU_BWD) || (MODE == DIG_EPI_ROWDOT) || (MODE == DIG_EPI_LINEAR && OUT_F32 && ep.residual != nullptr);
+  const bool has_bias = ep.bias != nullptr;
   const uint32_t row_s = (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7);
 
@@ -54,6 +58,12 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
   if (has_ld && half < NGT && lane == 0) {
     mbar_expect_tx(&st.ld_bar[0], kStageTileBytes);
     tma_load_2d_addr(st.stage_s, tm_aux, &st.ld_bar[0], n0 + half * G, row_base);
+#if DIG_EPI_EARLY_LD
+    if (half + 2 < NGT) {   // the second group's operand as well: both staging tiles are free here, and the load then has the accumulator
+      mbar_expect_tx(&st.ld_bar[1], kStageTileBytes);   // wait plus one whole group of math to arrive (it waited ~15 % of the epilogue's time)
+      tma_load_2d_addr(st.stage_s + kStageTileBytes, tm_aux, &st.ld_bar[1], n0 + (half + 2) * G, row_base);
+    }
+#endif
   }
   mbar_wait(tmem_full, full_phase);
   tc_fence_after();
@@ -72,7 +82,8 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
     const int gcol = n0 + gi * G;
     const uint32_t buf = st.stage_s + (uint32_t)((MODE == DIG_EPI_GELU) ? 0 : (k & 1)) * kStageTileBytes;
     const uint32_t buf2 = st.stage_s + kStageTileBytes;   // GELU forward: second output (post-activation)
-    if (k > 0) {  // the staging tile we are about to overwrite (or prefetch into) must have been read by its TMA store
+    constexpr int kFirstPrefetch = DIG_EPI_EARLY_LD ? 1 : 0;   // group k prefetches group k+1 unless the tile start already requested it
+    if (k > 0 && (!has_ld || (!last && k >= kFirstPrefetch))) {  // the staging tile we are about to overwrite (or prefetch into) must have been read by its TMA store
       if (lane == 0) {
         if (has_ld || MODE == DIG_EPI_GELU) tma_store_wait_read_all();
         else tma_store_wait_read_1();      // double-buffered: only the store issued two groups ago has to be done
@@ -80,7 +91,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
       __syncwarp();
     }
     if (has_ld) {
-      if (!last && lane == 0) {  // prefetch the next group's operand into the other staging tile
+      if (!last && k >= kFirstPrefetch && lane == 0) {  // prefetch the next group's operand into the other staging tile
         uint64_t* nb = &st.ld_bar[(k + 1) & 1];
         mbar_expect_tx(nb, kStageTileBytes);
         tma_load_2d_addr(st.stage_s + (uint32_t)((k + 1) & 1) * kStageTileBytes, tm_aux, nb, gcol + 2 * G, row_base);
@@ -114,8 +125,8 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
         if (alpha != 1.0f) { f.x *= alpha; f.y *= alpha; f.z *= alpha; f.w *= alpha; }
         const uint32_t a = buf + row_s + (((uint32_t)j ^ sw) << 4);
         if (MODE == DIG_EPI_LINEAR) {
-          if (ep.bias != nullptr && gcol + 4 * j < N) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 4 * j));
+          if (has_bias) {   // uniform (kernel parameter); columns past N are clipped by the TMA store, so their address is only clamped
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + min(gcol + 4 * j, N - 4)));
             f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
           }
           if (has_ld) {
@@ -138,9 +149,13 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] *= alpha;
         }
-        if (ep.bias != nullptr && gcol + 8 * j < N) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 8 * j));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol + 8 * j + 4));
+        // GELU forward: the host always supplies a bias (a zero vector if the caller passed none), so the loads sit in the same basic
+        // block as the polynomial and ptxas hoists them ahead of it; other modes: uniform branch on the kernel parameter.  Columns past
+        // N are clipped by the TMA store, so their bias address is only clamped.
+        if (MODE == DIG_EPI_GELU || has_bias) {
+          const int bc = min(gcol + 8 * j, N - 8);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + bc));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + bc + 4));
           f2_unpack(f2_add(f2_pack(f[0], f[1]), f2_pack(b0.x, b0.y)), f[0], f[1]);
           f2_unpack(f2_add(f2_pack(f[2], f[3]), f2_pack(b0.z, b0.w)), f[2], f[3]);
           f2_unpack(f2_add(f2_pack(f[4], f[5]), f2_pack(b1.x, b1.y)), f[4], f[5]);

@@ -2,7 +2,10 @@
 //   im2col for the 4x4 patch embed (F:188-195), LayerNorm forward/backward (F:134,140; M:424), window pooling
 //   (M:189-193), row gather / scatter-add for the masked-pixel decoder (M:563-570), column sums for bias
 //   gradients, BatchNorm1d batch statistics / apply / backward (M:463-482).
+#include <string.h>
+
 #include "common.cuh"
+#include "peer.cuh"
 #include "../../include/dig_b200.h"
 
 namespace dig {
@@ -346,7 +349,7 @@ struct ColVec<__nv_bfloat16> {
 template <typename T, bool SQUARES>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, float* __restrict__ out_sq, long long rows, int cols,
-              int rows_per_block) {
+              int rows_per_block, PeerReduce pr) {
   constexpr int V = ColVec<T>::kVec;
   __shared__ float sm[SQUARES ? 2 : 1][8][32 * V + 1];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -379,6 +382,7 @@ colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, fl
       if (SQUARES) atomicAdd(out_sq + gc, tq);
     }
   }
+  peer_allreduce_grid_tail(pr);   // SyncBatchNorm: the grid's last block sums [sum | sumsq] over the ranks through NVLink peer memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -444,7 +448,7 @@ __global__ void bn_running_kernel(const float* __restrict__ stats, float count, 
 // backward statistics: bstats = [sum dy | sum dy*xhat]  (dy already masked by the ReLU of this layer)
 __global__ void __launch_bounds__(256)
 bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats, float count, float eps,
-                    float* __restrict__ bstats, long long rows, int C, int rows_per_block) {
+                    float* __restrict__ bstats, long long rows, int C, int rows_per_block, PeerReduce pr) {
   __shared__ float sm[2][8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
@@ -470,6 +474,7 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
     atomicAdd(bstats + col, ts);
     atomicAdd(bstats + C + col, tq);
   }
+  peer_allreduce_grid_tail(pr);   // SyncBatchNorm backward: [sum dy | sum dy xhat] over the ranks; the rank-local sums go to pr.loc0 / loc1
 }
 
 // dx = gamma * rstd * (dy - sum_dy/n - xhat * sum_dy_xhat/n)   (bstats/count possibly all-reduced across ranks)
@@ -701,8 +706,8 @@ extern "C" int dig_scatter_add_rows(const float* src, const int32_t* idx, float*
   return 0;
 }
 
-extern "C" int dig_colsum(const void* x, int32_t x_is_fp32, int64_t ld, float* out, float* out_sq, int64_t rows, int32_t cols,
-                          void* stream) {
+static int colsum_launch(const void* x, int32_t x_is_fp32, int64_t ld, float* out, float* out_sq, int64_t rows, int32_t cols, const PeerReduce& pr,
+                         void* stream) {
   DIG_REQUIRE(x && out && rows > 0 && cols > 0, "dig_colsum: bad arguments");
   const int vec = x_is_fp32 ? 4 : 8;
   DIG_REQUIRE(cols % vec == 0 && ld % vec == 0 && ((uintptr_t)x & 15) == 0, "dig_colsum: cols/ld must be multiples of %d and x 16-byte aligned",
@@ -715,14 +720,43 @@ extern "C" int dig_colsum(const void* x, int32_t x_is_fp32, int64_t ld, float* o
   dim3 grid(gx, gy);
   cudaStream_t s = (cudaStream_t)stream;
   if (x_is_fp32) {
-    if (out_sq) colsum_kernel<float, true><<<grid, 256, 0, s>>>((const float*)x, ld, out, out_sq, rows, cols, rpb);
-    else colsum_kernel<float, false><<<grid, 256, 0, s>>>((const float*)x, ld, out, nullptr, rows, cols, rpb);
+    if (out_sq) colsum_kernel<float, true><<<grid, 256, 0, s>>>((const float*)x, ld, out, out_sq, rows, cols, rpb, pr);
+    else colsum_kernel<float, false><<<grid, 256, 0, s>>>((const float*)x, ld, out, nullptr, rows, cols, rpb, pr);
   } else {
-    if (out_sq) colsum_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, out_sq, rows, cols, rpb);
-    else colsum_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, nullptr, rows, cols, rpb);
+    if (out_sq) colsum_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, out_sq, rows, cols, rpb, pr);
+    else colsum_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, nullptr, rows, cols, rpb, pr);
   }
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+static PeerReduce no_peer() {
+  PeerReduce pr;
+  memset(&pr, 0, sizeof(pr));
+  return pr;
+}
+
+static int make_peer_reduce(PeerReduce* pr, const int64_t* bases, int32_t world, int32_t rank, int32_t channel, int64_t epoch, float* buf, int n,
+                            float* loc0, float* loc1, int nloc) {
+  DIG_REQUIRE(rank >= 0 && rank < world && channel >= 0 && channel < kPeerChannels && epoch >= 1, "peer: bad rank/channel/epoch");
+  DIG_REQUIRE(n > 0 && n <= kPeerMaxFloats, "peer: message of %d floats exceeds %d", n, kPeerMaxFloats);
+  if (int rc = fill_peer_table(&pr->pt, bases, world)) return rc;
+  pr->world = world; pr->rank = rank; pr->channel = channel; pr->epoch = (uint32_t)epoch; pr->buf = buf; pr->n = n;
+  pr->loc0 = loc0; pr->loc1 = loc1; pr->nloc = nloc;
+  return 0;
+}
+
+extern "C" int dig_colsum(const void* x, int32_t x_is_fp32, int64_t ld, float* out, float* out_sq, int64_t rows, int32_t cols,
+                          void* stream) {
+  return colsum_launch(x, x_is_fp32, ld, out, out_sq, rows, cols, no_peer(), stream);
+}
+
+extern "C" int dig_bn_stats_allreduce(const float* x, float* stats, int64_t rows, int32_t C, const int64_t* bases, int32_t world, int32_t rank,
+                                      int32_t channel, int64_t epoch, void* stream) {
+  DIG_REQUIRE(stats != nullptr && world > 1, "dig_bn_stats_allreduce: needs a stats buffer and world > 1");
+  PeerReduce pr;
+  if (int rc = make_peer_reduce(&pr, bases, world, rank, channel, epoch, stats, 2 * C, nullptr, nullptr, 0)) return rc;
+  return colsum_launch(x, 1, C, stats, stats + C, rows, C, pr, stream);
 }
 
 extern "C" int dig_bn_apply(const float* x, const float* stats, float count, const float* gamma, const float* beta, int32_t relu, float eps,
@@ -744,17 +778,31 @@ extern "C" int dig_bn_running(const float* stats, float count, float momentum, f
   return 0;
 }
 
-extern "C" int dig_bn_bwd_stats(const float* dy, const float* x, const float* stats, float count, float eps, float* bstats, int64_t rows,
-                                int32_t C, void* stream) {
+static int bn_bwd_stats_launch(const float* dy, const float* x, const float* stats, float count, float eps, float* bstats, int64_t rows,
+                               int32_t C, const PeerReduce& pr, void* stream) {
   DIG_REQUIRE(dy && x && stats && bstats && rows > 0 && C > 0 && count > 0, "dig_bn_bwd_stats: bad arguments");
   const int gx = (C + 31) / 32;
   int gy = (num_sms() * 8 + gx - 1) / gx;
   if (gy > (rows + 63) / 64) gy = (int)((rows + 63) / 64);
   if (gy < 1) gy = 1;
   const int rpb = (int)((rows + gy - 1) / gy);
-  bn_bwd_stats_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, count, eps, bstats, rows, C, rpb);
+  bn_bwd_stats_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, count, eps, bstats, rows, C, rpb, pr);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int dig_bn_bwd_stats(const float* dy, const float* x, const float* stats, float count, float eps, float* bstats, int64_t rows,
+                                int32_t C, void* stream) {
+  return bn_bwd_stats_launch(dy, x, stats, count, eps, bstats, rows, C, no_peer(), stream);
+}
+
+extern "C" int dig_bn_bwd_stats_allreduce(const float* dy, const float* x, const float* stats, float count, float eps, float* bstats,
+                                          float* dbeta_local, float* dgamma_local, int64_t rows, int32_t C, const int64_t* bases,
+                                          int32_t world, int32_t rank, int32_t channel, int64_t epoch, void* stream) {
+  DIG_REQUIRE(world > 1, "dig_bn_bwd_stats_allreduce: world must be > 1");
+  PeerReduce pr;
+  if (int rc = make_peer_reduce(&pr, bases, world, rank, channel, epoch, bstats, 2 * C, dbeta_local, dgamma_local, C)) return rc;
+  return bn_bwd_stats_launch(dy, x, stats, count, eps, bstats, rows, C, pr, stream);
 }
 
 extern "C" int dig_bn_bwd_apply(const float* dy, const float* x, const float* stats, const float* bstats, float count, const float* gamma,

@@ -1,0 +1,114 @@
+"""Host side of the NVLink peer-memory exchanges (dig_b200/csrc/peer.cu): one workspace per rank, IPC handles exchanged once through
+torch.distributed, then the SyncBatchNorm statistics (R:390) and the MoCo key all-gather (M:580-591) of every step are carried by
+dig_b200's own kernels -- no NCCL launch on the head chains.  torch.distributed remains the plumbing (rendezvous, the one-time handle
+exchange) and still carries the gradient all-reduce.
+
+Channels (one exchange sequence per stream, identical on every rank):
+  0  online forward  BatchNorm statistics      (main stream)
+  1  momentum forward BatchNorm statistics     (side stream)
+  2  backward BatchNorm statistics             (main stream)
+  3  key all-gather                            (side stream)
+"""
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+CH_ONLINE, CH_MOMENTUM, CH_BACKWARD, CH_KEYS = 0, 1, 2, 3
+MAX_FLOATS = 8192
+_MAX_RANKS = 8
+
+
+class PeerComm:
+    def __init__(self, device, key_table_bytes, group=None):
+        lib = ops.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _MAX_RANKS:
+            raise ops.DigError("peer-memory exchanges are built for one NVSwitch node (<= %d ranks)" % _MAX_RANKS)
+        self.key_table_bytes = int(key_table_bytes)
+        total, koff = ctypes.c_int64(), ctypes.c_int64()
+        ops._check(lib.dig_peer_workspace_bytes(self.key_table_bytes, ctypes.byref(total), ctypes.byref(koff)), "dig_peer_workspace_bytes")
+        self._own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        ok, err = 1, ""
+        try:
+            ops._check(lib.dig_peer_alloc(total.value, ctypes.byref(self._own), handle), "dig_peer_alloc")
+        except ops.DigError as e:
+            ok, err = 0, str(e)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, bytes(handle), torch.cuda.current_device(), os.uname().nodename), group=group)
+        self._mapped = []
+        bases = [0] * _MAX_RANKS
+        if all(g[0] for g in gathered) and len({g[3] for g in gathered}) == 1:
+            try:
+                for r, g in enumerate(gathered):
+                    if r == self.rank:
+                        bases[r] = self._own.value
+                    else:
+                        p = ctypes.c_void_p()
+                        ops._check(lib.dig_peer_open(g[1], ctypes.byref(p)), "dig_peer_open")
+                        self._mapped.append(p)
+                        bases[r] = p.value
+            except ops.DigError as e:
+                ok, err = 0, str(e)
+        else:
+            ok, err = 0, err or "a peer could not allocate its workspace, or the ranks span several hosts"
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)       # every rank maps every peer, or nobody uses the path
+        self.ok = bool(int(flag.item()))
+        self.error = err
+        self.bases = (ctypes.c_int64 * _MAX_RANKS)(*bases)
+        self.keys_offset = koff.value
+        self.epoch = [0, 0, 0, 0]
+        if not self.ok:
+            self.close()
+        dist.barrier(group=group)
+
+    def next_epoch(self, channel):
+        self.epoch[channel] += 1
+        return self.epoch[channel]
+
+    def key_table_ptr(self, epoch):
+        """Device address of this rank's key table for the exchange `epoch` ([2, W*Q, C] fp32, written by every rank's kernel)."""
+        return self._own.value + self.keys_offset + (epoch & 1) * self.key_table_bytes
+
+    def check(self):
+        e = ctypes.c_int32()
+        ops._check(ops.load().dig_peer_error(self.bases, self.world, self.rank, ctypes.byref(e)), "dig_peer_error")
+        if e.value:
+            raise ops.DigError("a peer-memory exchange timed out: a rank never arrived")
+
+    def close(self):
+        lib = ops.load()
+        for p in self._mapped:
+            lib.dig_peer_close(p)
+        self._mapped = []
+        if self._own:
+            lib.dig_peer_free(self._own)
+            self._own = ctypes.c_void_p()
+
+
+_comm = {}
+
+
+def get(device, key_table_bytes):
+    """The process-wide PeerComm (created collectively on first use; None when disabled with DIG_PEER=0, when the world is one rank, or
+    when the workspaces could not be mapped -- the callers then fall back to torch.distributed collectives)."""
+    if os.environ.get("DIG_PEER", "1") == "0" or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    if dist.get_backend() != "nccl":
+        return None
+    c = _comm.get("default")
+    if c is None or (c.ok and c.key_table_bytes < key_table_bytes):
+        if c is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            c.close()
+        c = PeerComm(device, key_table_bytes)
+        _comm["default"] = c
+        if not c.ok and dist.get_rank() == 0:
+            print("dig_b200: NVLink peer-memory exchanges unavailable (%s); using torch.distributed collectives" % c.error)
+    return c if c.ok else None

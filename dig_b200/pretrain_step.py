@@ -18,7 +18,7 @@ import math
 import torch
 import torch.distributed as dist
 
-from . import dist_layout, ops
+from . import dist_layout, ops, peer
 from .ops import call
 
 F32, BF16 = torch.float32, torch.bfloat16
@@ -118,6 +118,7 @@ class PretrainStep:
         self.forward_serial = 0
         self._n_masked = {}
         self._mask_err = None      # (event, pinned int32[1]) of the previous forward's dig_mask_to_index error flag
+        self._peer = None
         self._grad_flat = None
         # The momentum branch (EMA update + no-grad forward) and the online branch are independent until the InfoNCE logits: they run
         # on two streams so that one branch's HBM-bound kernels (LayerNorm, BatchNorm, casts) fill in under the other's GEMMs.
@@ -392,8 +393,15 @@ class PretrainStep:
             z = B.get("%s.z%d" % (tag, li), (rows, C), F32)
             ops.gemm(a, w, z)
             stats = B.zeroed("%s.st%d" % (tag, li), (2 * C,), F32, "fwd")
-            call("dig_colsum", z, 1, C, stats, stats[C:], rows, C)
-            count = dist_layout.sync_batch_stats(stats, rows) if self._bn_sync(bn) else float(rows)
+            pc = self._peer if (self._bn_sync(bn) and 2 * C <= peer.MAX_FLOATS) else None
+            if pc is not None:
+                # SyncBatchNorm (R:390): column sums + their cross-rank sum in ONE kernel over NVLink peer memory (csrc/peer.cu)
+                ch = peer.CH_MOMENTUM if tag.startswith("m.") else peer.CH_ONLINE
+                call("dig_bn_stats_allreduce", z, stats, rows, C, pc.bases, pc.world, pc.rank, ch, pc.next_epoch(ch))
+                count = float(rows * pc.world)
+            else:
+                call("dig_colsum", z, 1, C, stats, stats[C:], rows, C)
+                count = dist_layout.sync_batch_stats(stats, rows) if self._bn_sync(bn) else float(rows)
             a_out = B.get("%s.a%d" % (tag, li), (rows, C), BF16) if (not last or want_bf16_out) else None
             out_f32 = B.get("%s.out" % tag, (rows, C), F32) if last else None
             gamma, beta = (bn.weight, bn.bias) if bn.affine else (None, None)
@@ -413,12 +421,19 @@ class PretrainStep:
             sv = saved[li]
             C = w.shape[0]
             bst = B.zeroed("%s.bst%d" % (tag, li), (2 * C,), F32, "bwd")
-            call("dig_bn_bwd_stats", dy, sv["z"], sv["stats"], sv["count"], bn.eps, bst, rows, C)
-            if bn.affine:
-                grads[bnname + "bias"].copy_(bst[:C])
-                grads[bnname + "weight"].copy_(bst[C:])
-            if self._bn_sync(bn):
-                dist.all_reduce(bst)
+            pc = self._peer if (self._bn_sync(bn) and 2 * C <= peer.MAX_FLOATS) else None
+            if pc is not None:
+                # [sum dy | sum dy xhat] + cross-rank sum in one kernel; the rank-local sums are the BatchNorm bias / weight gradients
+                call("dig_bn_bwd_stats_allreduce", dy, sv["z"], sv["stats"], sv["count"], bn.eps, bst,
+                     grads[bnname + "bias"] if bn.affine else None, grads[bnname + "weight"] if bn.affine else None, rows, C,
+                     pc.bases, pc.world, pc.rank, peer.CH_BACKWARD, pc.next_epoch(peer.CH_BACKWARD))
+            else:
+                call("dig_bn_bwd_stats", dy, sv["z"], sv["stats"], sv["count"], bn.eps, bst, rows, C)
+                if bn.affine:
+                    grads[bnname + "bias"].copy_(bst[:C])
+                    grads[bnname + "weight"].copy_(bst[C:])
+                if self._bn_sync(bn):
+                    dist.all_reduce(bst)
             dz = B.get("%s.dz%d" % (tag, li), (rows, C), BF16)
             call("dig_bn_bwd_apply", dy, sv["z"], sv["stats"], bst, sv["count"], bn.weight if bn.affine else None, bn.eps, dz, None, rows, C)
             a_in = sv["a_in"]
@@ -444,6 +459,12 @@ class PretrainStep:
         if vis_mask_pos.shape[1] != 2:
             raise ops.DigError("num_view must be 2 (README.md:66), got %d" % vis_mask_pos.shape[1])
         self._check_mask_err()
+        if world > 1 and isinstance(model.predictor[1], torch.nn.SyncBatchNorm):
+            # collective on first use (every rank runs its first forward): NVLink peer-memory workspaces for the SyncBN / key exchanges;
+            # key table = [k1 of all ranks ; k2 of all ranks], Q = B * num_windows rows per rank and half
+            self._peer = peer.get(dev, 2 * world * (Bsz * self.num_windows) * int(model.encoder_projection_layer[-1].num_features) * 4)
+        else:
+            self._peer = None
         images = Bf.get("images", (S, 3, 32, 128), F32)
         images[:Bsz].copy_(image)
         images[Bsz:].copy_(aug_image)
@@ -487,10 +508,17 @@ class PretrainStep:
             k, _, _ = self._mlp_fwd(pooled_m, self._mlp_layers("momentum_projection_layer.", 3, model.momentum_projection_layer), "m.proj")
             R = k.shape[0]            # 2 * B * num_windows rows: [k1 ; k2]
             Q, C = R // 2, k.shape[1]
-            kn = Bf.get("kn", (R, C), F32)
-            call("dig_l2norm_fwd", k, kn, None, R, C)
-            k_all2 = dist_layout.gather_keys(kn, Bf.get("kall", (world, R, C), F32) if world > 1 else None,
-                                             Bf.get("kall2", (2, world * Q, C), F32) if world > 1 else None)       # M:580-591
+            pc = self._peer
+            if pc is not None and 2 * world * Q * C * 4 <= pc.key_table_bytes:
+                # F.normalize + concat_all_gather (M:446-447, M:580-591) in one kernel: every row goes straight into every rank's table
+                ep = pc.next_epoch(peer.CH_KEYS)
+                call("dig_peer_l2norm_allgather", pc.bases, pc.world, pc.rank, peer.CH_KEYS, ep, k, None, Q, C, pc.key_table_bytes)
+                k_all2 = pc.key_table_ptr(ep)
+            else:
+                kn = Bf.get("kn", (R, C), F32)
+                call("dig_l2norm_fwd", k, kn, None, R, C)
+                k_all2 = dist_layout.gather_keys(kn, Bf.get("kall", (world, R, C), F32) if world > 1 else None,
+                                                 Bf.get("kall2", (2, world * Q, C), F32) if world > 1 else None)       # M:580-591
             # operands of the logits GEMM (K-major [hi|lo|hi]) and of its gradient GEMM (MN-major planes), see dig_split_bf16x3
             Nk = world * Q
             k3 = Bf.get("nce.k3", (2, Nk, 3 * C), BF16)

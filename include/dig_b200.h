@@ -114,6 +114,37 @@ int dig_bn_bwd_stats(const float* dy, const float* x, const float* stats, float 
 int dig_bn_bwd_apply(const float* dy, const float* x, const float* stats, const float* bstats, float count,
                      const float* gamma, float eps, void* dx_bf16, float* dx_f32, int64_t rows, int32_t C, void* stream);
 
+/* ---- data-parallel exchanges carried by the kernels over NVLink peer memory (dig_b200/csrc/peer.cu) -------------------
+ * Replaces the torch.distributed calls of SyncBatchNorm (R:390: one tiny collective per BatchNorm layer, forward and
+ * backward) and concat_all_gather (M:580-591).  Every rank owns a workspace (dig_peer_alloc) whose IPC handle the ranks
+ * exchange out of band; `bases` is a HOST array of `world` int64 device addresses: this rank's own workspace at [rank],
+ * the mapped peer workspaces elsewhere.  `channel` (0..3) names an independent exchange sequence -- one per stream -- and
+ * `epoch` counts the exchanges of that channel from 1; every rank must issue the same sequence per channel.  A wait that
+ * times out (a peer died) sets an error word readable with dig_peer_error instead of hanging the GPU.                  */
+int dig_peer_workspace_bytes(int64_t key_table_bytes, int64_t* total_out, int64_t* keys_offset_out);
+int dig_peer_alloc(int64_t bytes, void** ptr_out, void* handle_out /* 64 bytes */);
+int dig_peer_open(const void* handle, void** ptr_out);
+int dig_peer_close(void* ptr);
+int dig_peer_free(void* ptr);
+int dig_peer_error(const int64_t* bases, int32_t world, int32_t rank, int32_t* err_out);
+/* buf[0..n) <- sum over ranks, added in rank order (bit-identical on every rank); n <= 8192. */
+int dig_peer_allreduce(const int64_t* bases, int32_t world, int32_t rank, int32_t channel, int64_t epoch, float* buf, int32_t n,
+                       void* stream);
+/* dig_colsum(x fp32 [rows,C]) into stats = [sum | sumsq] (+=) FUSED with the cross-rank sum of stats: the grid's last block
+ * pushes the 2C partials to every peer and adds the W partial vectors (SyncBatchNorm forward).                          */
+int dig_bn_stats_allreduce(const float* x, float* stats, int64_t rows, int32_t C, const int64_t* bases, int32_t world, int32_t rank,
+                           int32_t channel, int64_t epoch, void* stream);
+/* dig_bn_bwd_stats fused with the cross-rank sum of bstats (SyncBatchNorm backward); the rank-local sums -- the gradients
+ * of the BatchNorm bias and weight -- are written to dbeta_local / dgamma_local (fp32 [C], either may be NULL).         */
+int dig_bn_bwd_stats_allreduce(const float* dy, const float* x, const float* stats, float count, float eps, float* bstats,
+                               float* dbeta_local, float* dgamma_local, int64_t rows, int32_t C, const int64_t* bases,
+                               int32_t world, int32_t rank, int32_t channel, int64_t epoch, void* stream);
+/* F.normalize of this rank's keys x [2Q, C] = [k1 ; k2] (M:446-447) FUSED with concat_all_gather (M:580-591): every
+ * normalised row is stored into every rank's key table (slot epoch & 1 of the workspace's key area, key_table_bytes per
+ * slot) at [half][rank*Q + i][C]; when the kernel completes, the table holds all ranks' keys.  local_copy may be NULL.  */
+int dig_peer_l2norm_allgather(const int64_t* bases, int32_t world, int32_t rank, int32_t channel, int64_t epoch, const float* x,
+                              float* local_copy, int64_t Q, int32_t C, int64_t key_table_bytes, void* stream);
+
 /* elementwise fp32 -> bf16 (n % 4 == 0). */
 int dig_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 /* y (bf16 [rows,d]) = row_mask[r] ? 0 : x[r,:]  -- gradient that reaches the patch-embed GEMM past the mask-token mix (V:95-97). */
