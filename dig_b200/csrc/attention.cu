@@ -209,6 +209,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(kFwdPThreads, 1)
 attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
                         int heads, float scale, int num_items) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFwdPBuf + 2 * 16384);   // after the two 16 KB output staging tiles
@@ -256,6 +257,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
   constexpr uint32_t kColO = 192;
+  pdl_wait();   // prologue done: the qkv tensor written by the preceding GEMM is read from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -734,6 +736,7 @@ __global__ void __launch_bounds__(kBwdPThreads, 1)
 attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse, const float* __restrict__ Dsum, int heads,
                         float scale, int num_items) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdBars);
@@ -767,6 +770,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
+  pdl_wait();   // prologue done: qkv / dO / lse / D of earlier kernels are read from here on
   constexpr uint32_t cS = 0, cdP = 128, cdV = 256, cdK = 320, cdQ = 384;
 
   if (warp == 9) {
@@ -1000,7 +1004,7 @@ extern "C" int dig_attention_fwd(const void* qkv, void* out, float* lse, int64_t
     if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
     const int items = (int)(num_seqs * heads);
     const int ctas = items < num_sms() ? items : num_sms();
-    attn_fwd_persist_kernel<<<ctas, kFwdPThreads, smem, s>>>(tm, to, lse, heads, scale, items);
+    DIG_CHECK_CUDA(launch_pdl(attn_fwd_persist_kernel, dim3(ctas), dim3(kFwdPThreads), smem, s, tm, to, lse, heads, scale, items));
   } else if (!p_in_smem) {
     const int smem = 81920 + 1024 + 128;
     static bool set = false;
@@ -1061,7 +1065,7 @@ extern "C" int dig_attention_bwd_d(const void* qkv, const void* dout, const floa
   if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
   const int items = (int)(num_seqs * heads);
   const int ctas = items < num_sms() ? items : num_sms();
-  attn_bwd_persist_kernel<<<ctas, kBwdPThreads, smem, s>>>(tq, td, tg, lse, dsum, heads, scale, items);
+  DIG_CHECK_CUDA(launch_pdl(attn_bwd_persist_kernel, dim3(ctas), dim3(kBwdPThreads), smem, s, tq, td, tg, lse, dsum, heads, scale, items));
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -36,7 +36,34 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int is_fp32, uint64_t rows,
                  uint32_t box_rows, uint32_t box_cols);
 int num_sms();
 
+bool pdl_enabled();   // DIG_PDL (default on): launch with programmatic stream serialization
+
 #ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident as
+// soon as every CTA of the kernel before it in the stream has executed pdl_launch_dependents() (or exited), so its launch latency and
+// prologue -- barrier initialisation, TMEM allocation, descriptor prefetch: 1.5-3 us per launch, ~480 launches per step -- overlap the
+// tail of its predecessor.  pdl_wait() blocks until ALL prerequisite grids have completed and flushed their memory; every kernel calls
+// it before its first access to global memory, so the stream-order semantics are unchanged.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch helper: kern<<<grid, block, smem, stream>>>(args...) with the PDL attribute when enabled.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // small device utilities
 // ------------------------------------------------------------------------------------------------
@@ -87,15 +114,14 @@ __device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP, no rang
 }
 // exact-form (erf) GELU and its derivative, fp32 (nn.GELU, F:55).
 // gelu(x) = x (0.5 + xc P(xc^2) / Q(xc^2)), xc = clamp(x): a rational fit of (Phi(x) - 1/2)/x in x^2 with the 1/sqrt(2) argument scale and
-// the factor 0.5 folded into the coefficients.  Two fits (tools: the Lawson-weighted least-squares fit described in DESIGN.md):
-//   DIG_GELU_ORDER 3 (default): P3/Q3, |x| <= 4.75, max abs error of gelu 5.4e-6 -- 6 FMA + 1 MUFU per element.  The outputs are rounded
-//                               to bf16 (relative 2^-9 = 2e-3), three orders of magnitude above this error.
-//   DIG_GELU_ORDER 5          : P5/Q5, |x| <= 5.55, max abs error 3.9e-7 (round 1) -- 10 FMA + 1 MUFU.
-// The GEMM epilogues that evaluate them are FMA-pipe / issue bound, so the polynomial degree is step time.
+// the factor 0.5 folded into the coefficients (Lawson-weighted least-squares fits against scipy.special.erf, all Q coefficients positive).
+//   P5/Q5, |x| <= 5.55: max abs error 3.9e-7 -- the scalar functions below (row kernels, generic epilogue): 10 FMA + 1 MUFU per element.
+//   P3/Q3, |x| <= 4.75: max abs error of gelu 5.4e-6 -- the packed functions of the TMA GEMM epilogues (DIG_GELU_ORDER 3, default): 6 FMA +
+//   1 MUFU.  Those outputs are rounded to bf16 (relative 2^-9 = 2e-3), three orders of magnitude above the fit error, and the epilogues
+//   are FMA-pipe / issue bound, so the polynomial degree is step time.  DIG_GELU_ORDER 5 selects P5/Q5 there too (A/B switch).
 #ifndef DIG_GELU_ORDER
 #define DIG_GELU_ORDER 3
 #endif
-#if DIG_GELU_ORDER == 5
 #define DIG_GELU_CLAMP 5.5507882f
 #define DIG_GELU_P0 3.989422482e-01f
 #define DIG_GELU_P1 3.372429997e-02f
@@ -108,44 +134,33 @@ __device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP, no rang
 #define DIG_GELU_Q3 1.875976298e-03f
 #define DIG_GELU_Q4 7.307883344e-05f
 #define DIG_GELU_Q5 1.194982755e-06f
-#else
-#define DIG_GELU_CLAMP 4.75f
-#define DIG_GELU_P0 3.989111871e-01f
-#define DIG_GELU_P1 2.820760287e-02f
-#define DIG_GELU_P2 3.793992200e-03f
-#define DIG_GELU_P3 3.181064343e-05f
-#define DIG_GELU_Q1 2.372292233e-01f
-#define DIG_GELU_Q2 2.412535149e-02f
-#define DIG_GELU_Q3 1.133673430e-03f
-#endif
+#define DIG_GELU3_CLAMP 4.75f
+#define DIG_GELU3_P0 3.989111871e-01f
+#define DIG_GELU3_P1 2.820760287e-02f
+#define DIG_GELU3_P2 3.793992200e-03f
+#define DIG_GELU3_P3 3.181064343e-05f
+#define DIG_GELU3_Q1 2.372292233e-01f
+#define DIG_GELU3_Q2 2.412535149e-02f
+#define DIG_GELU3_Q3 1.133673430e-03f
 __device__ __forceinline__ float gelu_erf(float x) {
   const float xc = fminf(fmaxf(x, -DIG_GELU_CLAMP), DIG_GELU_CLAMP);
   const float t = xc * xc;
-#if DIG_GELU_ORDER == 5
   float p = DIG_GELU_P5;
   p = fmaf(p, t, DIG_GELU_P4);
   p = fmaf(p, t, DIG_GELU_P3);
-#else
-  float p = DIG_GELU_P3;
-#endif
   p = fmaf(p, t, DIG_GELU_P2);
   p = fmaf(p, t, DIG_GELU_P1);
   p = fmaf(p, t, DIG_GELU_P0);
-#if DIG_GELU_ORDER == 5
   float q = DIG_GELU_Q5;
   q = fmaf(q, t, DIG_GELU_Q4);
   q = fmaf(q, t, DIG_GELU_Q3);
-#else
-  float q = DIG_GELU_Q3;
-#endif
   q = fmaf(q, t, DIG_GELU_Q2);
   q = fmaf(q, t, DIG_GELU_Q1);
   q = fmaf(q, t, 1.0f);
   return x * fmaf(xc * p, rcp_approx(q), 0.5f);
 }
 // d/dx gelu_erf(x) = Phi(x) + x phi(x) = 0.5 + x P(x^2) / Q(x^2) on the clamped range (the odd part saturates at 0.5 beyond):
-//   order 3: |x| <= 4.5, max abs error 5.7e-5 (the product dy * gelu' is rounded to bf16);  order 5: |x| <= 6, 3.9e-7.
-#if DIG_GELU_ORDER == 5
+//   P5/Q5, |x| <= 6: max abs error 3.9e-7 (scalar);  P3/Q3, |x| <= 4.5: 5.7e-5 (packed; the product dy * gelu' is rounded to bf16).
 #define DIG_GELUG_CLAMP 6.0f
 #define DIG_GELUG_P0 7.978851765e-01f
 #define DIG_GELUG_P1 -3.087451237e-02f
@@ -158,36 +173,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
 #define DIG_GELUG_Q3 3.525759290e-03f
 #define DIG_GELUG_Q4 1.926611686e-04f
 #define DIG_GELUG_Q5 8.911869432e-06f
-#else
-#define DIG_GELUG_CLAMP 4.5f
-#define DIG_GELUG_P0 7.982111506e-01f
-#define DIG_GELUG_P1 -2.699143690e-02f
-#define DIG_GELUG_P2 1.421469197e-02f
-#define DIG_GELUG_P3 1.283048511e-04f
-#define DIG_GELUG_Q1 3.016213812e-01f
-#define DIG_GELUG_Q2 4.027552325e-02f
-#define DIG_GELUG_Q3 4.900047771e-03f
-#endif
+#define DIG_GELUG3_CLAMP 4.5f
+#define DIG_GELUG3_P0 7.982111506e-01f
+#define DIG_GELUG3_P1 -2.699143690e-02f
+#define DIG_GELUG3_P2 1.421469197e-02f
+#define DIG_GELUG3_P3 1.283048511e-04f
+#define DIG_GELUG3_Q1 3.016213812e-01f
+#define DIG_GELUG3_Q2 4.027552325e-02f
+#define DIG_GELUG3_Q3 4.900047771e-03f
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   x = fminf(fmaxf(x, -DIG_GELUG_CLAMP), DIG_GELUG_CLAMP);
   const float t = x * x;
-#if DIG_GELU_ORDER == 5
   float p = DIG_GELUG_P5;
   p = fmaf(p, t, DIG_GELUG_P4);
   p = fmaf(p, t, DIG_GELUG_P3);
-#else
-  float p = DIG_GELUG_P3;
-#endif
   p = fmaf(p, t, DIG_GELUG_P2);
   p = fmaf(p, t, DIG_GELUG_P1);
   p = fmaf(p, t, DIG_GELUG_P0);
-#if DIG_GELU_ORDER == 5
   float q = DIG_GELUG_Q5;
   q = fmaf(q, t, DIG_GELUG_Q4);
   q = fmaf(q, t, DIG_GELUG_Q3);
-#else
-  float q = DIG_GELUG_Q3;
-#endif
   q = fmaf(q, t, DIG_GELUG_Q2);
   q = fmaf(q, t, DIG_GELUG_Q1);
   q = fmaf(q, t, 1.0f);
@@ -221,27 +226,38 @@ __device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
 #define DIG_F2C(c) f2_pack(c, c)
 // (g0, g1) = gelu(x0, x1)
 __device__ __forceinline__ void gelu_erf_x2(float x0, float x1, float& g0, float& g1) {
+#ifdef DIG_GELU_IDENTITY   // experiment: epilogue without the activation arithmetic (what does the data movement alone cost?)
+  g0 = x0; g1 = x1; return;
+#endif
+#if DIG_GELU_ORDER == 5
   const float c0 = fminf(fmaxf(x0, -DIG_GELU_CLAMP), DIG_GELU_CLAMP);
   const float c1 = fminf(fmaxf(x1, -DIG_GELU_CLAMP), DIG_GELU_CLAMP);
+#else
+  const float c0 = fminf(fmaxf(x0, -DIG_GELU3_CLAMP), DIG_GELU3_CLAMP);
+  const float c1 = fminf(fmaxf(x1, -DIG_GELU3_CLAMP), DIG_GELU3_CLAMP);
+#endif
   const f32x2_t xc = f2_pack(c0, c1);
   const f32x2_t t = f2_mul(xc, xc);
 #if DIG_GELU_ORDER == 5
   f32x2_t p = f2_fma(DIG_F2C(DIG_GELU_P5), t, DIG_F2C(DIG_GELU_P4));
   p = f2_fma(p, t, DIG_F2C(DIG_GELU_P3));
   p = f2_fma(p, t, DIG_F2C(DIG_GELU_P2));
-#else
-  f32x2_t p = f2_fma(DIG_F2C(DIG_GELU_P3), t, DIG_F2C(DIG_GELU_P2));
-#endif
   p = f2_fma(p, t, DIG_F2C(DIG_GELU_P1));
   p = f2_fma(p, t, DIG_F2C(DIG_GELU_P0));
+#else
+  f32x2_t p = f2_fma(DIG_F2C(DIG_GELU3_P3), t, DIG_F2C(DIG_GELU3_P2));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELU3_P1));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELU3_P0));
+#endif
 #if DIG_GELU_ORDER == 5
   f32x2_t q = f2_fma(DIG_F2C(DIG_GELU_Q5), t, DIG_F2C(DIG_GELU_Q4));
   q = f2_fma(q, t, DIG_F2C(DIG_GELU_Q3));
   q = f2_fma(q, t, DIG_F2C(DIG_GELU_Q2));
-#else
-  f32x2_t q = f2_fma(DIG_F2C(DIG_GELU_Q3), t, DIG_F2C(DIG_GELU_Q2));
-#endif
   q = f2_fma(q, t, DIG_F2C(DIG_GELU_Q1));
+#else
+  f32x2_t q = f2_fma(DIG_F2C(DIG_GELU3_Q3), t, DIG_F2C(DIG_GELU3_Q2));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELU3_Q1));
+#endif
   q = f2_fma(q, t, DIG_F2C(1.0f));
   float q0, q1;
   f2_unpack(q, q0, q1);
@@ -250,27 +266,38 @@ __device__ __forceinline__ void gelu_erf_x2(float x0, float x1, float& g0, float
 }
 // (d0, d1) *= gelu'(x0, x1)
 __device__ __forceinline__ void gelu_erf_grad_mul_x2(float x0, float x1, float& d0, float& d1) {
+#ifdef DIG_GELU_IDENTITY
+  d0 += 0.f * x0; d1 += 0.f * x1; return;
+#endif
+#if DIG_GELU_ORDER == 5
   x0 = fminf(fmaxf(x0, -DIG_GELUG_CLAMP), DIG_GELUG_CLAMP);
   x1 = fminf(fmaxf(x1, -DIG_GELUG_CLAMP), DIG_GELUG_CLAMP);
+#else
+  x0 = fminf(fmaxf(x0, -DIG_GELUG3_CLAMP), DIG_GELUG3_CLAMP);
+  x1 = fminf(fmaxf(x1, -DIG_GELUG3_CLAMP), DIG_GELUG3_CLAMP);
+#endif
   const f32x2_t x = f2_pack(x0, x1);
   const f32x2_t t = f2_mul(x, x);
 #if DIG_GELU_ORDER == 5
   f32x2_t p = f2_fma(DIG_F2C(DIG_GELUG_P5), t, DIG_F2C(DIG_GELUG_P4));
   p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P3));
   p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P2));
-#else
-  f32x2_t p = f2_fma(DIG_F2C(DIG_GELUG_P3), t, DIG_F2C(DIG_GELUG_P2));
-#endif
   p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P1));
   p = f2_fma(p, t, DIG_F2C(DIG_GELUG_P0));
+#else
+  f32x2_t p = f2_fma(DIG_F2C(DIG_GELUG3_P3), t, DIG_F2C(DIG_GELUG3_P2));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELUG3_P1));
+  p = f2_fma(p, t, DIG_F2C(DIG_GELUG3_P0));
+#endif
 #if DIG_GELU_ORDER == 5
   f32x2_t q = f2_fma(DIG_F2C(DIG_GELUG_Q5), t, DIG_F2C(DIG_GELUG_Q4));
   q = f2_fma(q, t, DIG_F2C(DIG_GELUG_Q3));
   q = f2_fma(q, t, DIG_F2C(DIG_GELUG_Q2));
-#else
-  f32x2_t q = f2_fma(DIG_F2C(DIG_GELUG_Q3), t, DIG_F2C(DIG_GELUG_Q2));
-#endif
   q = f2_fma(q, t, DIG_F2C(DIG_GELUG_Q1));
+#else
+  f32x2_t q = f2_fma(DIG_F2C(DIG_GELUG3_Q3), t, DIG_F2C(DIG_GELUG3_Q2));
+  q = f2_fma(q, t, DIG_F2C(DIG_GELUG3_Q1));
+#endif
   q = f2_fma(q, t, DIG_F2C(1.0f));
   float q0, q1;
   f2_unpack(q, q0, q1);

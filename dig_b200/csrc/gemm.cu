@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux, GemmEpilogue ep, int M,
                   int N, int K, int split_k, int kb_per_split) {
+  pdl_launch_dependents();
   using S = GemmSmem<BN, TMA_EPI>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -87,6 +88,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
+  pdl_wait();   // prologue done (shared memory / TMEM only): global memory written by earlier kernels is touched from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -244,8 +246,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   }
   const long long work = (long long)num_m * num_n * split;
   const int grid = (int)(work < num_sms() ? work : num_sms());
-  kern<<<grid, kGemmThreads, S::kBytes, stream>>>(ta, tb, to, tx, ep, (int)g->M, (int)g->N, (int)g->K, split, per);
-  DIG_CHECK_CUDA(cudaGetLastError());
+  DIG_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), S::kBytes, stream, ta, tb, to, tx, ep, (int)g->M, (int)g->N, (int)g->K, split, per));
   return 0;
 }
 

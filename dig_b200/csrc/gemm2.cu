@@ -89,6 +89,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   constexpr uint32_t kIdesc = make_idesc_bf16(256, BN, A_MN, B_MN);
   constexpr int HB = BN / 2;  // B columns staged by each CTA
 
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_smem = reinterpret_cast<float*>(smem + kStages * S::kStage);
@@ -137,6 +138,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   cluster_sync_all();  // peer barriers are initialised before anyone arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
+  pdl_wait();   // everything above touched only this CTA's shared memory / TMEM; from here on global memory of earlier kernels is read
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs, own halves; the whole warp walks the loop, one elected lane issues) ==========
@@ -337,8 +339,7 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   const long long work = (long long)num_m * num_n * split;
   const int max_clusters = num_sms() / 2;
   const int clusters = (int)(work < max_clusters ? work : max_clusters);
-  kern<<<clusters * 2, kGemm2Threads, S::kBytes, stream>>>(ta, tb, to, tx, ep, (int)g->M, (int)g->N, (int)g->K, split, per);
-  DIG_CHECK_CUDA(cudaGetLastError());
+  DIG_CHECK_CUDA(launch_pdl(kern, dim3(clusters * 2), dim3(kGemm2Threads), S::kBytes, stream, ta, tb, to, tx, ep, (int)g->M, (int)g->N, (int)g->K, split, per));
   return 0;
 }
 

@@ -81,17 +81,20 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 // dx = dres + LN_bwd(dy);  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy;  dxsum += sum_rows dx
 // (dy is w.r.t. the LN output, or the GELU(LN) output when GELU).  One warp per row, D/32 contiguous-by-4 columns per lane,
 // every global access 128-bit (64-bit for the bf16 streams); all loads of a row are issued before the first reduction.
-template <int D, bool GELU>
+// RBF: the residual gradient `dres` is a bf16 stream (dig_layernorm_bwd_bf16res) instead of fp32.
+template <int D, bool GELU, bool RBF>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     const float* dres, float* dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
+                     const void* dres_v, float* dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows) {
   constexpr int NV = D / 128;  // float4 groups per lane
   __shared__ float part[3 * D];
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) part[i] = 0.f;
   __syncthreads();
+  pdl_wait();
   float4 ag[NV], ab[NV], ax[NV], gm[NV], bt[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -107,7 +110,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
       xv[k] = *reinterpret_cast<const float4*>(x + row * D + c);
       const uint2 t = *reinterpret_cast<const uint2*>(dy + row * D + c);
       dv[k] = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
-      rv[k] = dres ? *reinterpret_cast<const float4*>(dres + row * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (RBF) {
+        const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dres_v) + row * D + c);
+        rv[k] = make_float4(bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y));
+      } else {
+        const float* dres = reinterpret_cast<const float*>(dres_v);
+        rv[k] = dres ? *reinterpret_cast<const float4*>(dres + row * D + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     const float mu = mean[row], rs = rstd[row];
     float c1 = 0.f, c2 = 0.f;
@@ -170,11 +179,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restri
 }
 
 // generic-width variant (d % 64 == 0, d <= 512), used for the 192-wide pix_decoder LayerNorm
-template <bool GELU>
+template <bool GELU, bool RBF>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                             const float* dres, float* dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
+                             const void* dres_v, float* dx_f32, __nv_bfloat16* __restrict__ dx_bf16,
                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int d) {
   extern __shared__ float part[];  // [3][d] block partials (dgamma | dbeta | column sums of dx)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -221,8 +230,11 @@ layernorm_bwd_generic_kernel(const __nv_bfloat16* __restrict__ dy, const float* 
         const int c = k * 64 + lane * 2;
         float o0 = rs * (g[k].x - c1 - xh[k].x * c2);
         float o1 = rs * (g[k].y - c1 - xh[k].y * c2);
-        if (dres) {
-          const float2 r = *reinterpret_cast<const float2*>(dres + row * d + c);
+        if (RBF) {
+          const uint32_t r = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(dres_v) + row * d + c);
+          o0 += bf16_lo(r); o1 += bf16_hi(r);
+        } else if (dres_v) {
+          const float2 r = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(dres_v) + row * d + c);
           o0 += r.x; o1 += r.y;
         }
         ax[k].x += o0; ax[k].y += o1;
@@ -346,7 +358,7 @@ struct ColVec<__nv_bfloat16> {
   }
 };
 
-template <typename T, bool SQUARES>
+template <typename T, bool SQUARES, bool PEER>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, float* __restrict__ out_sq, long long rows, int cols,
               int rows_per_block, PeerReduce pr) {
@@ -382,7 +394,7 @@ colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, fl
       if (SQUARES) atomicAdd(out_sq + gc, tq);
     }
   }
-  peer_allreduce_grid_tail(pr);   // SyncBatchNorm: the grid's last block sums [sum | sumsq] over the ranks through NVLink peer memory
+  if (PEER) peer_allreduce_grid_tail(pr);   // SyncBatchNorm: the grid's last block sums [sum | sumsq] over the ranks through NVLink peer memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,6 +458,7 @@ __global__ void bn_running_kernel(const float* __restrict__ stats, float count, 
 }
 
 // backward statistics: bstats = [sum dy | sum dy*xhat]  (dy already masked by the ReLU of this layer)
+template <bool PEER>
 __global__ void __launch_bounds__(256)
 bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats, float count, float eps,
                     float* __restrict__ bstats, long long rows, int C, int rows_per_block, PeerReduce pr) {
@@ -474,7 +487,7 @@ bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
     atomicAdd(bstats + col, ts);
     atomicAdd(bstats + C + col, tq);
   }
-  peer_allreduce_grid_tail(pr);   // SyncBatchNorm backward: [sum dy | sum dy xhat] over the ranks; the rank-local sums go to pr.loc0 / loc1
+  if (PEER) peer_allreduce_grid_tail(pr);   // SyncBatchNorm backward: [sum dy | sum dy xhat] over the ranks; the rank-local sums go to pr.loc0 / loc1
 }
 
 // dx = gamma * rstd * (dy - sum_dy/n - xhat * sum_dy_xhat/n)   (bstats/count possibly all-reduced across ranks)
@@ -528,6 +541,16 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 }
 
 // y (bf16) = row_mask[r] ? 0 : x  (gradient reaching the patch-embed GEMM: masked tokens were replaced by mask_token, V:95-97)
+__global__ void zero_masked_rows_bf16_kernel(const __nv_bfloat16* __restrict__ x, const uint8_t* __restrict__ row_mask,
+                                             __nv_bfloat16* __restrict__ y, long long rows, int d) {
+  const int dv = d >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * dv) return;
+  uint4 v = reinterpret_cast<const uint4*>(x)[i];
+  if (row_mask[i / dv]) v = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4*>(y)[i] = v;
+}
+
 __global__ void zero_masked_rows_kernel(const float* __restrict__ x, const uint8_t* __restrict__ row_mask, __nv_bfloat16* __restrict__ y,
                                         long long rows, int d) {
   const int dv = d >> 2;
@@ -585,6 +608,8 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                          __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, float eps) {
   constexpr int d = NC * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -633,9 +658,8 @@ extern "C" int dig_layernorm_fwd(const float* x, const float* gamma, const float
   if (!gelu && (d == 384 || d == 512) && (((uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 && ((uintptr_t)y & 7) == 0) {
     long long want = (rows + 7) / 8;
     const int vgrid = (int)(want < (long long)num_sms() * 4 ? want : (long long)num_sms() * 4);   // 4 resident blocks of 8 warps per SM (58-70 registers)
-    if (d == 384) dig::layernorm_fwd_vec_kernel<3><<<vgrid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, eps);
-    else dig::layernorm_fwd_vec_kernel<4><<<vgrid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, rows, eps);
-    DIG_CHECK_CUDA(cudaGetLastError());
+    if (d == 384) DIG_CHECK_CUDA(launch_pdl(dig::layernorm_fwd_vec_kernel<3>, dim3(vgrid), dim3(256), 0, (cudaStream_t)stream, x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, (long long)rows, eps));
+    else DIG_CHECK_CUDA(launch_pdl(dig::layernorm_fwd_vec_kernel<4>, dim3(vgrid), dim3(256), 0, (cudaStream_t)stream, x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, (long long)rows, eps));
     return 0;
   }
   const int grid = blocks_for(rows, 8);
@@ -645,28 +669,48 @@ extern "C" int dig_layernorm_fwd(const float* x, const float* gamma, const float
   return 0;
 }
 
-extern "C" int dig_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                                 const float* beta, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                                 float* dxsum, int64_t rows, int32_t d, int32_t gelu, void* stream) {
+static int layernorm_bwd_launch(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                const void* dres, bool dres_bf16, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum,
+                                int64_t rows, int32_t d, int32_t gelu, void* stream) {
   DIG_REQUIRE(dy && x && mean && rstd && gamma && dgamma && dbeta && rows > 0, "dig_layernorm_bwd: bad arguments");
   DIG_REQUIRE(d % 64 == 0 && d <= 512, "dig_layernorm_bwd: d must be a multiple of 64 and <= 512 (got %d)", d);
   DIG_REQUIRE(!gelu || beta, "dig_layernorm_bwd: gelu variant needs beta");
+  DIG_REQUIRE(!dres_bf16 || (dres && !gelu), "dig_layernorm_bwd_bf16res: needs dres and has no gelu variant");
   int grid = num_sms() * 4;
   if (grid > blocks_for(rows, 8)) grid = blocks_for(rows, 8);
   cudaStream_t s = (cudaStream_t)stream;
   const __nv_bfloat16* dyh = (const __nv_bfloat16*)dy;
   __nv_bfloat16* dxh = (__nv_bfloat16*)dx_bf16;
-  if (!gelu && d == 384) {
-    layernorm_bwd_kernel<384, false><<<grid, 256, 0, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows);
+  const size_t sm = 3 * d * sizeof(float);
+#define DIG_LN_ARGS dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, (long long)rows
+  if (dres_bf16) {
+    if (d == 384) DIG_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<384, false, true>, dim3(grid), dim3(256), 0, s, DIG_LN_ARGS));
+    else if (d == 512) DIG_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<512, false, true>, dim3(grid), dim3(256), 0, s, DIG_LN_ARGS));
+    else layernorm_bwd_generic_kernel<false, true><<<grid, 256, sm, s>>>(DIG_LN_ARGS, d);
+  } else if (!gelu && d == 384) {
+    DIG_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<384, false, false>, dim3(grid), dim3(256), 0, s, DIG_LN_ARGS));
   } else if (!gelu && d == 512) {
-    layernorm_bwd_kernel<512, false><<<grid, 256, 0, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows);
+    DIG_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<512, false, false>, dim3(grid), dim3(256), 0, s, DIG_LN_ARGS));
   } else {
-    const size_t sm = 3 * d * sizeof(float);
-    if (gelu) layernorm_bwd_generic_kernel<true><<<grid, 256, sm, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows, d);
-    else layernorm_bwd_generic_kernel<false><<<grid, 256, sm, s>>>(dyh, x, mean, rstd, gamma, beta, dres, dx_f32, dxh, dgamma, dbeta, dxsum, rows, d);
+    if (gelu) layernorm_bwd_generic_kernel<true, false><<<grid, 256, sm, s>>>(DIG_LN_ARGS, d);
+    else layernorm_bwd_generic_kernel<false, false><<<grid, 256, sm, s>>>(DIG_LN_ARGS, d);
   }
+#undef DIG_LN_ARGS
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int dig_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                                 float* dxsum, int64_t rows, int32_t d, int32_t gelu, void* stream) {
+  return layernorm_bwd_launch(dy, x, mean, rstd, gamma, beta, dres, false, dx_f32, dx_bf16, dgamma, dbeta, dxsum, rows, d, gelu, stream);
+}
+
+extern "C" int dig_layernorm_bwd_bf16res(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                         const void* dres_bf16, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows,
+                                         int32_t d, void* stream) {
+  DIG_REQUIRE(dres_bf16 && dx_bf16, "dig_layernorm_bwd_bf16res: dres_bf16 and dx_bf16 are required");
+  return layernorm_bwd_launch(dy, x, mean, rstd, gamma, nullptr, dres_bf16, true, nullptr, dx_bf16, dgamma, dbeta, dxsum, rows, d, 0, stream);
 }
 
 extern "C" int dig_pool_fwd(const float* x0, const float* x1, int64_t split, void* out, int64_t num_seqs, int32_t d, int32_t num_windows,
@@ -719,12 +763,16 @@ static int colsum_launch(const void* x, int32_t x_is_fp32, int64_t ld, float* ou
   const int rpb = (int)((rows + gy - 1) / gy);
   dim3 grid(gx, gy);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_is_fp32) {
-    if (out_sq) colsum_kernel<float, true><<<grid, 256, 0, s>>>((const float*)x, ld, out, out_sq, rows, cols, rpb, pr);
-    else colsum_kernel<float, false><<<grid, 256, 0, s>>>((const float*)x, ld, out, nullptr, rows, cols, rpb, pr);
+  const bool peer = pr.world > 1;
+  if (peer) {      // the fused exchange is built for the BatchNorm statistics call (fp32 input, sums and squares)
+    DIG_REQUIRE(x_is_fp32 && out_sq, "dig_colsum: the peer variant needs fp32 input and out_sq");
+    colsum_kernel<float, true, true><<<grid, 256, 0, s>>>((const float*)x, ld, out, out_sq, rows, cols, rpb, pr);
+  } else if (x_is_fp32) {
+    if (out_sq) colsum_kernel<float, true, false><<<grid, 256, 0, s>>>((const float*)x, ld, out, out_sq, rows, cols, rpb, pr);
+    else colsum_kernel<float, false, false><<<grid, 256, 0, s>>>((const float*)x, ld, out, nullptr, rows, cols, rpb, pr);
   } else {
-    if (out_sq) colsum_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, out_sq, rows, cols, rpb, pr);
-    else colsum_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, nullptr, rows, cols, rpb, pr);
+    if (out_sq) colsum_kernel<__nv_bfloat16, true, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, out_sq, rows, cols, rpb, pr);
+    else colsum_kernel<__nv_bfloat16, false, false><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, nullptr, rows, cols, rpb, pr);
   }
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -786,7 +834,8 @@ static int bn_bwd_stats_launch(const float* dy, const float* x, const float* sta
   if (gy > (rows + 63) / 64) gy = (int)((rows + 63) / 64);
   if (gy < 1) gy = 1;
   const int rpb = (int)((rows + gy - 1) / gy);
-  bn_bwd_stats_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, count, eps, bstats, rows, C, rpb, pr);
+  if (pr.world > 1) bn_bwd_stats_kernel<true><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, count, eps, bstats, rows, C, rpb, pr);
+  else bn_bwd_stats_kernel<false><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(dy, x, stats, count, eps, bstats, rows, C, rpb, pr);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -824,6 +873,14 @@ extern "C" int dig_cast_f32_bf16(const float* x, void* y, int64_t n, void* strea
 extern "C" int dig_zero_masked_rows(const float* x, const uint8_t* row_mask, void* y, int64_t rows, int32_t d, void* stream) {
   DIG_REQUIRE(x && row_mask && y && rows > 0 && d % 4 == 0, "dig_zero_masked_rows: bad arguments");
   zero_masked_rows_kernel<<<blocks_for(rows * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, row_mask, (__nv_bfloat16*)y, rows, d);
+  DIG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dig_zero_masked_rows_bf16(const void* x, const uint8_t* row_mask, void* y, int64_t rows, int32_t d, void* stream) {
+  DIG_REQUIRE(x && row_mask && y && rows > 0 && d % 8 == 0, "dig_zero_masked_rows_bf16: bad arguments");
+  zero_masked_rows_bf16_kernel<<<blocks_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, row_mask,
+                                                                                                  (__nv_bfloat16*)y, rows, d);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

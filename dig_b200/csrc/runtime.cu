@@ -3,6 +3,7 @@
 // loads on a machine without a GPU driver).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/dig_b200.h"
@@ -67,6 +68,15 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int is_fp32, uint64_t rows,
   DIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu stride=%llu box=%ux%u base=%p fp32=%d", (int)r,
               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_elems, box_rows, box_cols, base, is_fp32);
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DIG_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

@@ -122,10 +122,17 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
         moco_m = utils.adjust_moco_momentum(epoch + 1.0 * step / n_it, args) if args.use_moco_m_cos else args.moco_m
         metric_logger.update(moco_m=moco_m)
 
-        images, aug_images, mask = batch
-        images = images.to(device, non_blocking=True)
-        aug_images = aug_images.to(device, non_blocking=True)
-        mask = mask.to(device, non_blocking=True).flatten(1).to(torch.bool).view(images.shape[0], args.num_view, -1)
+        stage = getattr(args, "gpu_input_stage", None)
+        if stage is not None and len(batch) == 2:
+            # the loader ships the two views as uint8 [B,32,128,3]; ToTensor / Normalize / RandomGrayscale and the random
+            # masks (datasets.py:27-49, dataset_image.py:39-52, masking_generator.py:12-46) run on the device (dig_b200/input_stage.py)
+            world, rank = utils.get_world_size(), utils.get_rank()
+            images, aug_images, mask = stage(batch[0], batch[1], sample0=(it * world + rank) * batch[0].shape[0], step=it)
+        else:
+            images, aug_images, mask = batch
+            images = images.to(device, non_blocking=True)
+            aug_images = aug_images.to(device, non_blocking=True)
+            mask = mask.to(device, non_blocking=True).flatten(1).to(torch.bool).view(images.shape[0], args.num_view, -1)
         if args.only_mim_on_ori_img:
             mask[:, 1, :].fill_(0)                                                                    # E:103-104
 

@@ -44,7 +44,7 @@ class _Gemm(ctypes.Structure):
 EPI_LINEAR, EPI_GELU, EPI_GELU_BWD, EPI_RELU_MASK, EPI_ROWDOT = 0, 1, 2, 3, 5
 
 
-_CTYPE = {"int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "float": ctypes.c_float, "int": ctypes.c_int}
+_CTYPE = {"double": ctypes.c_double, "int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "float": ctypes.c_float, "int": ctypes.c_int}
 
 
 def header_path():

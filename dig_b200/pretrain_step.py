@@ -125,6 +125,9 @@ class PretrainStep:
         import os
         self._two_streams = os.environ.get("DIG_TWO_STREAMS", "1") != "0"
         self._always_cast = os.environ.get("DIG_ALWAYS_CAST", "0") == "1"
+        # The running gradient of the residual stream through the encoder backward is a bf16 stream (each LayerNorm backward reads it and
+        # writes the next one; it is the dgrad GEMM operand anyway) -- DIG_BF16_GRAD_STREAM=0 keeps the fp32 copy alongside (round 1).
+        self._bf16_grad_stream = os.environ.get("DIG_BF16_GRAD_STREAM", "1") != "0"
         self._side = torch.cuda.Stream(device=self.device) if self._two_streams else None
 
     # ------------------------------------------------------------------ parameter bookkeeping
@@ -336,9 +339,14 @@ class PretrainStep:
                 ops.gemm(dh, a["ln2"], grads[nm + "mlp.fc1.weight"], a_mn_major=True, b_mn_major=True, split_k=-1)
             on_side(mlp_wgrads, [("gb", gi), ("dh", hi)])
             ops.gemm(dh, bw["f1w"], dln, b_mn_major=True)
+            gprev = gb                      # the running residual gradient (bf16 stream): read by the LayerNorm backward, then dead
             gi, gb = take("gb")
-            call("dig_layernorm_bwd", dln, a["xm"], a["mean2"], a["rstd2"], bw["n2w"], None, g, g, gb,
-                 grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], grads[nm + "attn.proj.bias"], M, d, 0)
+            if self._bf16_grad_stream:
+                call("dig_layernorm_bwd_bf16res", dln, a["xm"], a["mean2"], a["rstd2"], bw["n2w"], gprev, gb,
+                     grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], grads[nm + "attn.proj.bias"], M, d)
+            else:
+                call("dig_layernorm_bwd", dln, a["xm"], a["mean2"], a["rstd2"], bw["n2w"], None, g, g, gb,
+                     grads[nm + "norm2.weight"], grads[nm + "norm2.bias"], grads[nm + "attn.proj.bias"], M, d, 0)
             # ---- attention (F:87-125) ----
             # output-projection dgrad; its epilogue also emits D = rowsum(dO o O) per (token, head) for the attention backward
             ops.gemm(gb, bw["pw"], dat, b_mn_major=True, epilogue=ops.EPI_ROWDOT, aux=a["att"], rowdot=dsum)
@@ -358,9 +366,14 @@ class PretrainStep:
             on_side(qkv_wgrads, [("dqkv", qi)])
             ops.gemm(dqkv, bw["qkvw"], dln, b_mn_major=True)
             prev_b2 = grads[W["blocks"][l - 1]["name"] + "mlp.fc2.bias"] if l > 0 else None
+            gprev = gb
             gi, gb = take("gb")
-            call("dig_layernorm_bwd", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], None, g, g, gb,
-                 grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], prev_b2, M, d, 0)
+            if self._bf16_grad_stream:
+                call("dig_layernorm_bwd_bf16res", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], gprev, gb,
+                     grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], prev_b2, M, d)
+            else:
+                call("dig_layernorm_bwd", dln, a["x"], a["mean1"], a["rstd1"], bw["n1w"], None, g, g, gb,
+                     grads[nm + "norm1.weight"], grads[nm + "norm1.bias"], prev_b2, M, d, 0)
             # block l is final once this LayerNorm backward (chain) and its weight gradients (side stream) are done
             self._allreduce_segment("block%d" % l, stream=side)
         if two:
@@ -368,10 +381,14 @@ class PretrainStep:
         # ---- patch embed + mask token (F:190-196, V:95-99); pos_embed carries no gradient (V:99 detach) ----
         pre = W["pre"]
         gz = B.get("bw.gz", (M, d), BF16)
-        call("dig_zero_masked_rows", g, sv["mask"], gz, M, d)
-        call("dig_colsum", gz, 0, d, grads[pre + "patch_embed.proj.bias"], None, M, d)
         tot = B.zeroed("bw.tot", (d,), F32, "bwd")
-        call("dig_colsum", g, 1, d, tot, None, M, d)
+        if self._bf16_grad_stream:
+            call("dig_zero_masked_rows_bf16", gb, sv["mask"], gz, M, d)
+            call("dig_colsum", gb, 0, d, tot, None, M, d)
+        else:
+            call("dig_zero_masked_rows", g, sv["mask"], gz, M, d)
+            call("dig_colsum", g, 1, d, tot, None, M, d)
+        call("dig_colsum", gz, 0, d, grads[pre + "patch_embed.proj.bias"], None, M, d)
         torch.sub(tot, grads[pre + "patch_embed.proj.bias"], out=grads[pre + "mask_token"].view(-1))
         ops.gemm(gz, sv["a0"], grads[pre + "patch_embed.proj.weight"].view(d, 48), a_mn_major=True, b_mn_major=True,
                  split_k=-1)

@@ -90,6 +90,12 @@ int dig_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
 int dig_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* beta, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                       float* dxsum, int64_t rows, int32_t d, int32_t gelu, void* stream);
+/* The same with the residual gradient carried as a bf16 stream (encoder blocks: the running gradient of the residual stream is the
+ * bf16 operand of the next dgrad GEMM anyway, so it is read and written once as bf16 instead of twice as fp32 + once as bf16:
+ * 250 instead of 400 bytes per element-row pair).  dx_bf16 = bf16(dres_bf16 + dLN(dy)); statistics and sums stay fp32.      */
+int dig_layernorm_bwd_bf16res(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                              const void* dres_bf16, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, int64_t rows,
+                              int32_t d, void* stream);
 /* PatchNet pooling without patch transformer (M:189-193): [S,8,32,d] fp32 -> mean over 8 x (32/num_windows)
  * token windows -> bf16 [S*num_windows, d].  Sequences < split come from x0, the others from x1.     */
 int dig_pool_fwd(const float* x0, const float* x1, int64_t split, void* out, int64_t num_seqs, int32_t d,
@@ -149,9 +155,21 @@ int dig_peer_l2norm_allgather(const int64_t* bases, int32_t world, int32_t rank,
 int dig_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 /* y (bf16 [rows,d]) = row_mask[r] ? 0 : x[r,:]  -- gradient that reaches the patch-embed GEMM past the mask-token mix (V:95-97). */
 int dig_zero_masked_rows(const float* x, const uint8_t* row_mask, void* y, int64_t rows, int32_t d, void* stream);
+int dig_zero_masked_rows_bf16(const void* x, const uint8_t* row_mask, void* y, int64_t rows, int32_t d, void* stream);
 /* Boolean mask [B,256] -> row indices in boolean-mask order (M:569): idx[b*n_per+j] = b*256 + j-th set position;
  * err[0] = 1 if some sample does not have exactly n_per set bits.                                       */
 int dig_mask_to_index(const uint8_t* mask, int32_t* idx, int32_t* err, int32_t B, int32_t n_per, void* stream);
+
+/* ---- GPU-side input stage ------------------------------------------------------------------------
+ * transforms.ToTensor + Normalize(0.5, 0.5) of both 32x128 views (dataset/datasets.py:30-37, dataset/dataset_image.py:39-52):
+ * uint8 [B,32,128,3] -> fp32 [B,3,32,128] = ((x/255) - 0.5)/0.5, bit-identical to torchvision; RandomGrayscale(gray_p) of the
+ * augmented view (dataset_image.py:46, PIL luma) decided per sample by a counter-based draw from (seed, step, sample0 + b).   */
+int dig_normalize_views(const uint8_t* img_u8, const uint8_t* aug_u8, float* img_out, float* aug_out, int64_t B, float gray_p,
+                        int64_t seed, int64_t step, int64_t sample0, void* stream);
+/* RandomMaskingGenerator (masking_generator.py:12-46): per (sample, view) a uniformly random n_mask-subset of the 256 patch
+ * positions, as uint8 0/1 [B,V,256] and/or the loader's float64 layout; reproducible from (seed, step, sample0 + b, view).    */
+int dig_random_masks(uint8_t* mask_u8, double* mask_f64, int64_t B, int32_t num_view, int32_t n_mask, int64_t seed, int64_t step,
+                     int64_t sample0, void* stream);
 
 /* ---- losses (fp32) --------------------------------------------------------------------------------- */
 /* F.normalize(x, dim=1) (M:446-447) and its backward, dx = (dy - y<y,dy>) * inv_norm * gscale[0] (gscale may be NULL). */

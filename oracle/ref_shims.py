@@ -258,6 +258,28 @@ def import_runner(dataset_len=24):
         import dig_b200.registry as dig_registry
         import dig_b200.modeling  # noqa: F401
         _MODEL_REGISTRY.update(dig_registry._MODELS)      # timm.models.create_model (stub) -> this repo's drop-in factories
+
+        class _Tee:      # utils/logging.py:27-67 Logger closes sys.stdout in __del__ (it would take pytest's capture file with it)
+            def __init__(self, fpath=None):
+                self.console = sys.stdout
+                self.file = open(fpath, "w") if fpath else None
+
+            def write(self, msg):
+                self.console.write(msg)
+                if self.file is not None:
+                    self.file.write(msg)
+
+            def flush(self):
+                self.console.flush()
+                if self.file is not None:
+                    self.file.flush()
+
+            def close(self):
+                if self.file is not None:
+                    self.file.close()
+                    self.file = None
+
+        runner.Logger = _Tee
     finally:
         sys.path[:] = saved_path
     return runner

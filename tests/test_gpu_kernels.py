@@ -167,6 +167,36 @@ def test_layernorm_forward_backward(ops, d, gelu):
     assert torch.allclose(d2, dx, atol=1e-5)
 
 
+@pytest.mark.parametrize("d", [384, 512, 192])
+def test_layernorm_backward_with_bf16_residual_gradient_stream(ops, d):
+    """dig_layernorm_bwd_bf16res: dx_bf16 = bf16(dres_bf16 + dLN(dy)); out of place and in place (the single-stream schedule)."""
+    torch.manual_seed(6)
+    rows = 777
+    x = rnd(rows, d, scale=2.0).requires_grad_(True)
+    g = (1 + 0.1 * rnd(d)).requires_grad_(True)
+    b = (0.1 * rnd(d)).requires_grad_(True)
+    y = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.call("dig_layernorm_fwd", x.detach(), g.detach(), b.detach(), y, mean, rstd, rows, d, 1e-6, 0)
+    dy, dres = rnd(rows, d, dtype=torch.bfloat16), rnd(rows, d, dtype=torch.bfloat16)
+    torch.nn.functional.layer_norm(x, (d,), g, b, 1e-6).backward(dy.float())
+    ref = x.grad + dres.float()
+    dxb = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    dg, db, dsum = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    ops.call("dig_layernorm_bwd_bf16res", dy, x.detach(), mean, rstd, g.detach(), dres, dxb, dg, db, dsum, rows, d)
+    assert torch.allclose(dxb.float(), ref, atol=3e-2, rtol=1e-2)
+    assert torch.allclose(dg, g.grad, atol=1e-3, rtol=1e-4) and torch.allclose(db, b.grad, atol=1e-3, rtol=1e-4)
+    assert torch.allclose(dsum, ref.sum(0), atol=2e-3, rtol=1e-4)          # column sums of the fp32 values before rounding
+    inpl = dres.clone()
+    ops.call("dig_layernorm_bwd_bf16res", dy, x.detach(), mean, rstd, g.detach(), inpl, inpl, dg, db, None, rows, d)
+    assert torch.equal(inpl, dxb)
+    # masked-row zeroing of a bf16 stream
+    mask = (torch.rand(rows, device="cuda") < 0.5).to(torch.uint8)
+    gz = torch.empty_like(dxb)
+    ops.call("dig_zero_masked_rows_bf16", dxb, mask, gz, rows, d)
+    assert torch.equal(gz, torch.where(mask.bool()[:, None], torch.zeros_like(dxb), dxb))
+
+
 def test_batchnorm_forward_backward(ops):
     torch.manual_seed(6)
     rows, C = 517, 512

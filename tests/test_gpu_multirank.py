@@ -40,19 +40,26 @@ def _step(net, model, img, aug, mk):
 
 def _worker(rank, world, port, q):
     try:
+        import datetime
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
         torch.cuda.set_device(rank)
         dev = torch.device("cuda", rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-        import __graft_entry__ as ge
-        if rank == 0:
-            ge.build()
-        dist.barrier()
         from oracle import restatement as R
-        from dig_b200.parallel import DigDataParallel
         img, aug, mask = R.synthetic_batch(world * B, seed=3)
         mk = mask.clone()
         mk[:, 1, :] = False
+        ref = None
+        if rank == 0:
+            # the single-process step over the concatenated batch, BEFORE the process group exists (with a group of two ranks the model
+            # would -- correctly -- wait for the other rank's keys)
+            import __graft_entry__ as ge
+            ge.build()
+            single = _model().to(dev)
+            ref = _step(single, single, img.to(dev), aug.to(dev), mk.to(dev))
+            del single
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.barrier()
+        from dig_b200.parallel import DigDataParallel
         sl = slice(rank * B, (rank + 1) * B)
         res = {}
         for tag, env in (("peer", "1"), ("nccl", "0")):
@@ -68,9 +75,6 @@ def _worker(rank, world, port, q):
             res[tag + "_avg"] = (t / world).tolist()
         out = None
         if rank == 0:
-            single = _model().to(dev)
-            ref = _step(single, single, img.to(dev), aug.to(dev), mk.to(dev))
-
             def rel(a, b):
                 return float((a - b).norm() / (b.norm() + 1e-20))
             out = {"peer_used": res["peer_peer_used"], "nccl_peer_used": res["nccl_peer_used"], "loss_single": ref[:3],
@@ -98,9 +102,11 @@ def test_two_ranks_equal_one_rank_with_the_concatenated_batch():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=900) for _ in procs), key=lambda r: r[0])
+    res = sorted((q.get(timeout=400) for _ in procs), key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
+        if p.is_alive():
+            p.kill()
     assert all(r[1] for r in res), res
     out = res[0][2]
     print(out["loss_single"], out["loss_peer"], out["loss_nccl"])

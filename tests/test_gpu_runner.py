@@ -22,15 +22,18 @@ MODEL = "pretrain_simmim_moco_ori_vit_tiny_patch4_32x128"
 def _argv(out_dir, epochs, batch=8):
     return ["run_mae_pretraining_moco.py", "--batch_size", str(batch), "--epochs", str(epochs), "--model", MODEL, "--mask_ratio", "0.7",
             "--num_view", "2", "--moco_dim", "256", "--moco_mlp_dim", "4096", "--moco_m", "0.99", "--moco_t", "0.2", "--num_windows", "4",
-            "--patchnet_name", "no_patchtrans", "--loss_weight_pixel", "1.0", "--loss_weight_contrast", "0.1", "--only_mim_on_ori_img", "1",
+            "--patchnet_name", "no_patchtrans", "--loss_weight_pixel", "1.0", "--loss_weight_contrast", "0.1", "--only_mim_on_ori_img",
             "--contrast_warmup_steps", "0", "--warmup_epochs", "0", "--opt", "adamw", "--opt_betas", "0.9", "0.999", "--lr", "1.5e-4",
             "--weight_decay", "0.05", "--drop_path", "0.0", "--num_workers", "0", "--output_dir", out_dir, "--log_dir", "", "--device", "cuda",
             "--save_ckpt_freq", "1", "--seed", "0"]
 
 
 def _run_main(runner, argv):
-    old_argv, old_stdout = sys.argv, sys.stdout
+    old_argv, old_stdout, old_load = sys.argv, sys.stdout, torch.load
     sys.argv = argv
+    # the reference's auto_load_model (U:581-669) calls torch.load(path, map_location='cpu') on a checkpoint that holds its argparse
+    # Namespace; torch >= 2.6 defaults to weights_only=True.  One more version shim of the kind SURVEY.md 8(c) lists.
+    torch.load = lambda *a, **k: old_load(*a, **{**k, "weights_only": k.get("weights_only", False)})
     try:
         args = runner.get_args()
         if not args.log_dir:
@@ -38,7 +41,7 @@ def _run_main(runner, argv):
         os.makedirs(args.output_dir, exist_ok=True)
         runner.main(args)
     finally:
-        sys.argv, sys.stdout = old_argv, old_stdout
+        sys.argv, sys.stdout, torch.load = old_argv, old_stdout, old_load
     return args
 
 
