@@ -81,7 +81,7 @@ def _worker(rank, world, port, q):
                    "loss_peer": res["peer_avg"], "loss_nccl": res["nccl_avg"],
                    "grad_rel_peer_vs_single": {n: rel(res["peer"][3][n], ref[3][n]) for n in ref[3]},
                    "grad_rel_peer_vs_nccl": {n: rel(res["peer"][3][n], res["nccl"][3][n]) for n in ref[3]},
-                   "bn_rel_peer_vs_single": {k: rel(res["peer"][4][k], ref[4][k]) for k in ref[4]}}
+                   "bn_absdiff_peer_vs_single": {k: float((res["peer"][4][k] - ref[4][k]).abs().max()) for k in ref[4]}}
         # gradients are identical on every rank after the averaging
         chk = torch.stack([g.double().sum() for g in res["peer"][3].values()]).sum().reshape(1)
         both = [torch.zeros_like(chk) for _ in range(world)]
@@ -123,4 +123,6 @@ def test_two_ranks_equal_one_rank_with_the_concatenated_batch():
         json.dump(out, open(os.path.join(d, "multirank_parity.json"), "w"), indent=1)
     # run-to-run noise of the atomically accumulated statistics is ~1e-2 on head tensors at small batch
     assert worst < 8e-2 and worst_pn < 8e-2
-    assert max(out["bn_rel_peer_vs_single"].values()) < 1e-3
+    # BatchNorm running statistics (global over the ranks == over the concatenated batch); absolute, because several running means are
+    # exact zeros up to rounding (the predictor's first Linear sees a zero-mean input: the projector ends in BatchNorm(affine=False))
+    assert max(out["bn_absdiff_peer_vs_single"].values()) < 2e-3
