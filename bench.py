@@ -14,6 +14,7 @@ the timed region.  Rank 0 prints ONE JSON line.  Besides the contract keys it ca
   cpu_baseline        the reference step on the host cores (bounded sample)
   gpu_eager_baseline  the oracle port of the reference step, torch eager + bf16 autocast (cuBLASLt / ATen) on the same GPU
   vit_base            the ViT-B(512) bs=64 configuration (BASELINE configs[3]) measured the same way, fewer steps
+  finetune            the fine-tuning step (BASELINE configs[4]): ViT-S encoder + tf_decoder, bs=256/GPU
   torch_ddp           (N > 1) the same step wrapped by torch DistributedDataParallel, what the unmodified runner constructs (R:391)
 """
 import argparse
@@ -265,6 +266,46 @@ class Workload:
         out = self.net(self.img_d, self.aug_d, self.mask_d, 0.99, True)
         lp = masked_pixel_mse(out["vis_out"][0], self.img_d, self.mask_d[:, 0])
         loss = out["contra_loss"] * 0.1 + lp
+        self.opt.zero_grad()
+        self.scaler(loss, self.opt, clip_grad=None, parameters=self.model.parameters())
+        return loss
+
+
+class FinetuneWorkload:
+    """BASELINE configs[4]: fine-tune simmim_vit_small_patch4_32x128 + tf_decoder, bs=256/GPU (dropout 0): DigRecModel forward,
+    SeqCrossEntropyLoss, backward, grad-norm, fused AdamW on a resident synthetic batch (images U(-1,1), 25-position labels)."""
+
+    def __init__(self, B, dev, rank, world):
+        import torch
+        from dig_b200.finetune import DigRecModel
+        from dig_b200.optim import FusedAdamW
+        from dig_b200.utils import NativeScalerWithGradNormCount
+        self.B, self.dev = B, dev
+        torch.manual_seed(0)
+        model = DigRecModel("simmim_vit_small_patch4_32x128").to(dev).train()
+        self.model = self.net = model
+        if world > 1:      # run_class_finetuning.py:497 (mask_token gets no gradient here)
+            self.net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], find_unused_parameters=True)
+        decay, no_decay = [], []
+        for n, p in model.named_parameters():
+            if p.requires_grad:
+                (no_decay if (p.dim() == 1 or n.endswith(".bias")) else decay).append(p)
+        self.opt = FusedAdamW([{"params": decay, "weight_decay": 0.05, "lr_scale": 1.0}, {"params": no_decay, "weight_decay": 0.0, "lr_scale": 1.0}],
+                              lr=1e-4 * B * world / 256, betas=(0.9, 0.999), eps=1e-8)
+        self.scaler = NativeScalerWithGradNormCount()
+        g = torch.Generator().manual_seed(7 + rank)
+        self.img = (torch.rand(B, 3, 32, 128, generator=g) * 2 - 1).to(dev)
+        lens = torch.randint(1, 26, (B,), generator=g)
+        tgt = torch.randint(0, 94, (B, 25), generator=g)
+        pos = torch.arange(25)[None, :]
+        tgt = torch.where(pos == (lens[:, None] - 1), torch.full_like(tgt, 94), tgt)
+        tgt = torch.where(pos >= lens[:, None], torch.full_like(tgt, 95), tgt)
+        self.tgt, self.lens = tgt.to(dev), lens.to(dev)
+
+    def step(self):
+        from dig_b200.finetune import seq_cross_entropy
+        logits = self.net((self.img, self.tgt, self.lens))[0]
+        loss, _ = seq_cross_entropy(logits, self.tgt, self.lens)
         self.opt.zero_grad()
         self.scaler(loss, self.opt, clip_grad=None, parameters=self.model.parameters())
         return loss
@@ -537,6 +578,22 @@ def gpu_arm(a):
             except Exception as e:
                 extras["vit_base"] = {"error": repr(e)}
             sync_all(world)
+
+    # BASELINE configs[4]: the fine-tuning step, bs=256/GPU, every rank takes part
+    if not a.no_extras and a.model == MODEL and os.environ.get("DIG_BENCH_FINETUNE", "1") != "0":
+        try:
+            wlf = FinetuneWorkload(256, dev, rank, world)
+            msf, lossf, _ = timed_steps(wlf, max(5, a.steps // 2), 3, world)
+            gf = 43.1     # GFLOP per sample: encoder 3 x 12.089 + linear_norm / decoder / classifier 3 x 2.27 (2 FLOP per MAC, bwd = 2 x fwd)
+            extras["finetune"] = {"value": 256 * world / (msf * 1e-3), "unit": "samples/s", "ms_per_step": msf, "loss": lossf,
+                                  "config": {"workload": "simmim_vit_small_patch4_32x128 + tf_decoder bs=256/GPU, max_len 25, dropout 0, "
+                                                         "fwd+bwd+AdamW (BASELINE configs[4]), resident inputs", "global_batch": 256 * world,
+                                             "dp_wrapper": "torch DistributedDataParallel" if world > 1 else None},
+                                  "whole_step_frac": (256 / (msf * 1e-3)) * gf * 1e9 / (peaks()[0] * 1e12)}
+            del wlf
+        except Exception as e:
+            extras["finetune"] = {"error": repr(e)}
+        sync_all(world)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

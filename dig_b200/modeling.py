@@ -82,7 +82,7 @@ def sinusoid_table(n_position, d_hid):
 class _Encoder(_Holder):
     """Holder for PretrainVisionTransformerEncoder's tensors (V:27-73)."""
 
-    def __init__(self, img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, eps):
+    def __init__(self, img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, eps, final_norm=False):
         super().__init__()
         self.embed_dim = self.num_features = embed_dim
         self.num_heads = num_heads
@@ -90,7 +90,8 @@ class _Encoder(_Holder):
         self.mask_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.pos_embed = sinusoid_table(self.patch_embed.num_patches, embed_dim)  # plain attr, V:48
         self.blocks = nn.ModuleList([_Block(embed_dim, mlp_ratio, eps) for _ in range(depth)])
-        self.norm = nn.Identity()
+        # the pre-training model strips the final norm (M:362 sets encoder.norm = Identity); the fine-tuning encoder keeps it (V:57,104)
+        self.norm = nn.LayerNorm(embed_dim, eps=eps) if final_norm else nn.Identity()
         self.head = nn.Identity()
         # V:63-73: xavier on every Linear (bias 0), LayerNorm 1/0, in module-traversal order
         for mod in self.modules():

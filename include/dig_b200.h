@@ -197,6 +197,30 @@ int dig_masked_mse(const float* pred, const float* images, const int32_t* idx, f
                    void* stream);
 int dig_scale_by_device_scalar(const float* x, const float* s, float* y, int64_t n, void* stream);
 
+/* ---- fine-tuning step: transformer decoder pieces ----------------------------------------------------
+ * The decoder's Linears run on dig_gemm; these are the small irregular ops around them (fp32 on CUDA cores, T <= 32 queries).
+ * x[b*T+t,:] = emb[tok,:] + pos[t,:], tok = <BOS> start_idx at t = 0, targets[b,t-1] after (models/decoder.py:173-178, 212-214).  */
+int dig_embed_pos_fwd(const int64_t* targets, const float* emb, const float* pos, float* x, int32_t B, int32_t T, int32_t D,
+                      int32_t start_idx, void* stream);
+int dig_embed_bwd(const float* dx, const int64_t* targets, float* demb, int32_t B, int32_t T, int32_t D, int32_t start_idx,
+                  void* stream);
+/* MultiHeadAttention core (models/transformer_layer.py:241-281), head_dim 64, Lq <= 32, Lk <= 256: q/k/v/out are bf16 with
+ * head h in columns h*64..h*64+63 (leading dimensions in elements); lse fp32 [B,H,Lq] is saved for the backward; lens != NULL
+ * applies get_pad_mask & get_subsequent_mask (transformer_layer.py:433-456; self-attention, Lq == Lk); maps (may be NULL)
+ * fp32 [B,Lq,Lk] += attention weights averaged over the heads (vis_attn_maps, :270).                                        */
+int dig_dec_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo,
+                          float* lse, const int64_t* lens, float* maps, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                          void* stream);
+int dig_dec_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* out,
+                          int64_t ldo, const void* dout, int64_t lddo, const float* lse, const int64_t* lens, void* dq, int64_t lddq,
+                          void* dk, int64_t lddk, void* dv, int64_t lddv, int32_t B, int32_t H, int32_t Lq, int32_t Lk, float scale,
+                          void* stream);
+/* SeqCrossEntropyLoss, sample_normalize (loss/seqCrossEntropyLoss.py:47-63): loss[0] += sum over positions t < lens[b] of
+ * -log softmax(logits[b,t,:C])[targets[b,t]] / B; dlogits (may be NULL, fp32 [B*T, ldd], zero beyond C and for padded
+ * positions) = d loss / d logits; pred (may be NULL) = arg-max class per position (engine_for_finetuning.py:162-164).         */
+int dig_seq_cross_entropy(const float* logits, int64_t ld, const int64_t* targets, const int64_t* lens, float* loss, float* dlogits,
+                          int64_t ldd, int32_t* pred, int32_t B, int32_t T, int32_t C, void* stream);
+
 /* ---- multi-tensor parameter kernels (pointer tables on the device, see dig_b200/csrc/optim.cu) ------ */
 int dig_mt_chunk(void); /* elements per thread block in the blk_* tables */
 int dig_mt_cast_bf16(const int64_t* src, const int64_t* dst, const int64_t* numel, const int32_t* blk_tensor,

@@ -156,6 +156,32 @@ def import_reference():
     return _REF_CACHE
 
 
+_REF_FT_CACHE = None
+
+
+def import_reference_finetune():
+    """Returns (models.model_builder module, SeqCrossEntropyLoss class) of the REFERENCE (fine-tuning path)."""
+    global _REF_FT_CACHE
+    if _REF_FT_CACHE is not None:
+        return _REF_FT_CACHE
+    import_reference()
+    saved = {n: sys.modules.pop(n) for n in _SHADOWED + ("models", "engine_for_finetuning") if n in sys.modules}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import importlib
+        importlib.import_module("modeling_pretrain_vit")          # registers simmim_vit_*_patch4_32x128 (V:114-136)
+        mb = importlib.import_module("models.model_builder")
+        crit = importlib.import_module("loss.seqCrossEntropyLoss").SeqCrossEntropyLoss
+        assert os.path.abspath(mb.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), mb.__file__
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for n in _SHADOWED:
+            sys.modules.pop(n, None)
+        sys.modules.update({k: v for k, v in saved.items() if k in _SHADOWED})
+    _REF_FT_CACHE = (mb, crit)
+    return _REF_FT_CACHE
+
+
 def create_reference_model(name="pretrain_simmim_moco_ori_vit_small_patch4_32x128", seed=0, **over):
     """Factory call exactly as run_mae_pretraining_moco.get_model makes it (R:278-294)."""
     M = import_reference()[0]
