@@ -69,9 +69,10 @@ __global__ void __launch_bounds__(kDecThreads)
 dec_attn_fwd_kernel(DecAttnArgs a) {
   extern __shared__ uint8_t smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
-  __nv_bfloat16* sV = sK + kDecMaxK * kKRow;
-  float* sQ = reinterpret_cast<float*>(sV + kDecMaxK * kKRow);   // [4 warps][64]
-  float* sP = sQ + 4 * kDecHd;                                  // [4 warps][256]
+  const int LkP = (a.Lk + 3) & ~3;                               // shared-memory sizes follow the actual key count (occupancy)
+  __nv_bfloat16* sV = sK + LkP * kKRow;
+  float* sQ = reinterpret_cast<float*>(sV + LkP * kKRow);        // [4 warps][64]
+  float* sP = sQ + 4 * kDecHd;                                  // [4 warps][LkP]
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   load_kv_tile(a.k + (long long)b * a.Lk * a.ldk + h * kDecHd, a.ldk, a.Lk, sK);
@@ -79,7 +80,7 @@ dec_attn_fwd_kernel(DecAttnArgs a) {
   __syncthreads();
   const int len = a.lens ? (int)a.lens[b] : a.Lk;
   float* q = sQ + warp * kDecHd;
-  float* p = sP + warp * kDecMaxK;
+  float* p = sP + warp * LkP;
   for (int i = warp; i < a.Lq; i += 4) {
     const long long qrow = (long long)b * a.Lq + i;
     {
@@ -149,11 +150,12 @@ __global__ void __launch_bounds__(kDecThreads)
 dec_attn_bwd_kernel(DecAttnBwdArgs a) {
   extern __shared__ uint8_t smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
-  __nv_bfloat16* sV = sK + kDecMaxK * kKRow;
-  float* sQ = reinterpret_cast<float*>(sV + kDecMaxK * kKRow);   // [Lq][64] unscaled q
+  const int LkP = (a.Lk + 3) & ~3;
+  __nv_bfloat16* sV = sK + LkP * kKRow;
+  float* sQ = reinterpret_cast<float*>(sV + LkP * kKRow);        // [Lq][64] unscaled q
   float* sdO = sQ + kDecMaxQ * kDecHd;                           // [Lq][64]
-  float* sP = sdO + kDecMaxQ * kDecHd;                           // [Lq][Lk]
-  float* sdS = sP + kDecMaxQ * kDecMaxK;                         // [Lq][Lk]
+  float* sP = sdO + kDecMaxQ * kDecHd;                           // [Lq][LkP]
+  float* sdS = sP + kDecMaxQ * LkP;                              // [Lq][LkP]
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   load_kv_tile(a.k + (long long)b * a.Lk * a.ldk + h * kDecHd, a.ldk, a.Lk, sK);
@@ -179,8 +181,8 @@ dec_attn_bwd_kernel(DecAttnBwdArgs a) {
       const uint32_t wo = *reinterpret_cast<const uint32_t*>(a.out + row * a.ldo + h * kDecHd + lane * 2);
       dsum = warp_sum(bf16_lo(wo) * dO[lane * 2] + bf16_hi(wo) * dO[lane * 2 + 1]);
     }
-    float* p = sP + i * kDecMaxK;
-    float* ds = sdS + i * kDecMaxK;
+    float* p = sP + i * LkP;
+    float* ds = sdS + i * LkP;
     for (int j = lane; j < a.Lk; j += 32) {
       float pj = 0.f, dsj = 0.f;
       if (j < nvis) {
@@ -216,7 +218,7 @@ dec_attn_bwd_kernel(DecAttnBwdArgs a) {
     const int j = w >> 5, c2 = w & 31;
     float v0 = 0.f, v1 = 0.f, k0 = 0.f, k1 = 0.f;
     for (int i = 0; i < a.Lq; ++i) {
-      const float pj = sP[i * kDecMaxK + j], dsj = sdS[i * kDecMaxK + j];
+      const float pj = sP[i * LkP + j], dsj = sdS[i * LkP + j];
       v0 = fmaf(pj, sdO[i * kDecHd + c2 * 2], v0);
       v1 = fmaf(pj, sdO[i * kDecHd + c2 * 2 + 1], v1);
       k0 = fmaf(dsj, sQ[i * kDecHd + c2 * 2], k0);
@@ -270,8 +272,8 @@ seq_ce_kernel(const float* __restrict__ logits, long long ld, const long long* _
   }
 }
 
-static size_t dec_fwd_smem() { return (size_t)2 * kDecMaxK * kKRow * 2 + 4 * kDecHd * 4 + 4 * kDecMaxK * 4; }
-static size_t dec_bwd_smem() { return (size_t)2 * kDecMaxK * kKRow * 2 + 2 * kDecMaxQ * kDecHd * 4 + 2 * kDecMaxQ * kDecMaxK * 4; }
+static size_t dec_fwd_smem(int Lk) { const size_t k = (Lk + 3) & ~3; return 2 * k * kKRow * 2 + 4 * kDecHd * 4 + 4 * k * 4; }
+static size_t dec_bwd_smem(int Lk) { const size_t k = (Lk + 3) & ~3; return 2 * k * kKRow * 2 + 2 * kDecMaxQ * kDecHd * 4 + 2 * kDecMaxQ * k * 4; }
 
 }  // namespace dig
 
@@ -314,10 +316,10 @@ extern "C" int dig_dec_attention_fwd(const void* q, int64_t ldq, const void* k, 
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
   static bool attr = false;
   if (!attr) {
-    DIG_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_fwd_smem()));
+    DIG_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_fwd_smem(kDecMaxK)));
     attr = true;
   }
-  dec_attn_fwd_kernel<<<B * H, kDecThreads, dec_fwd_smem(), (cudaStream_t)stream>>>(a);
+  dec_attn_fwd_kernel<<<B * H, kDecThreads, dec_fwd_smem(Lk), (cudaStream_t)stream>>>(a);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -336,10 +338,10 @@ extern "C" int dig_dec_attention_bwd(const void* q, int64_t ldq, const void* k, 
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv; a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
   static bool attr = false;
   if (!attr) {
-    DIG_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_bwd_smem()));
+    DIG_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_bwd_smem(kDecMaxK)));
     attr = true;
   }
-  dec_attn_bwd_kernel<<<B * H, kDecThreads, dec_bwd_smem(), (cudaStream_t)stream>>>(a);
+  dec_attn_bwd_kernel<<<B * H, kDecThreads, dec_bwd_smem(Lk), (cudaStream_t)stream>>>(a);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -268,12 +268,22 @@ class FinetuneStep(PretrainStep):
             self._ln(x1, N_[p + "norm2.weight"], N_[p + "norm2.bias"], h2, m2, r2, eps=eps)
             qc = Bf.get(t + "qc", (Md, dm), BF16)
             ops.gemm(h2, S_[p + "enc_attn.linear_q.weight"], qc)
-            kv = Bf.get(t + "kv", (M, 2 * dm), BF16)
+            # Encoder-decoder attention on the fused tcgen05 attention kernel of the encoder: the T <= 32 decoder queries of a sample are
+            # placed in the first T rows of a 256-row query tile (the other rows stay zero and their outputs are never read), K and V of the
+            # 256 memory tokens are written by the fused k|v projection GEMM straight into the q|k|v layout the kernel reads.
+            qkvx = self._zero_once(t + "qkvx", (M, 3 * dm), BF16)
+            kv = qkvx[:, dm:]
             ops.gemm(mem, S_[p + "enc_kv"], kv)
+            qkvx.view(B, TOK, 3 * dm)[:, :T, :dm].copy_(qc.view(B, T, dm))
+            attx = Bf.get(t + "attx", (M, dm), BF16)
+            lse_c = Bf.get(t + "lse_c", (B, H, TOK), F32)
+            ops.attention_fwd(qkvx, attx, lse_c, H, self.scale)
             ca = Bf.get(t + "ca", (Md, dm), BF16)
-            lse_c = Bf.get(t + "lse_c", (B, H, T), F32)
-            call("dig_dec_attention_fwd", qc, dm, kv, 2 * dm, kv[:, dm:], 2 * dm, ca, dm, lse_c, None, maps if l == self.nl - 1 else None,
-                 B, H, T, TOK, self.scale)
+            ca.view(B, T, dm).copy_(attx.view(B, TOK, dm)[:, :T])
+            if need_maps and l == self.nl - 1:      # head-averaged attention weights of the last layer (visualisation only): CUDA-core kernel
+                scratch = Bf.get("d.maps_o", (Md, dm), BF16)
+                call("dig_dec_attention_fwd", qc, dm, kv, 3 * dm, qkvx[:, 2 * dm:], 3 * dm, scratch, dm, Bf.get("d.maps_lse", (B, H, T), F32), None,
+                     maps, B, H, T, TOK, self.scale)
             x2 = Bf.get(t + "x2", (Md, dm), F32)
             ops.gemm(ca, S_[p + "enc_attn.fc.weight"], x2, residual=x1)
             h3 = Bf.get(t + "h3", (Md, dm), BF16)
@@ -284,7 +294,7 @@ class FinetuneStep(PretrainStep):
             ops.gemm(h3, S_[p + "mlp.w_1.weight"], f1, bias=N_[p + "mlp.w_1.bias"], epilogue=ops.EPI_GELU, aux=fpre)
             x3 = Bf.get(t + "x3", (Md, dm), F32)
             ops.gemm(f1, S_[p + "mlp.w_2.weight"], x3, bias=N_[p + "mlp.w_2.bias"], residual=x2)
-            layers.append(dict(x0=xd, h1=h1, m1=m1, r1=r1, qkv=qkv, sa=sa, lse_s=lse_s, x1=x1, h2=h2, m2=m2, r2=r2, qc=qc, kv=kv, ca=ca,
+            layers.append(dict(x0=xd, h1=h1, m1=m1, r1=r1, qkv=qkv, sa=sa, lse_s=lse_s, x1=x1, h2=h2, m2=m2, r2=r2, qc=qc, qkvx=qkvx, attx=attx, ca=ca,
                                lse_c=lse_c, x2=x2, h3=h3, m3=m3, r3=r3, fpre=fpre, f1=f1, p=p))
             xd = x3
         hf = Bf.get("d.hf", (Md, dm), BF16)
@@ -357,10 +367,12 @@ class FinetuneStep(PretrainStep):
             ops.gemm(gxb, S_[p + "enc_attn.fc.weight"], dca, b_mn_major=True)
             wgrad(gxb, a["ca"], grads[p + "enc_attn.fc.weight"])
             dqc = Bf.get("b.dqc", (Md, dm), BF16)
-            dkv = Bf.get("b.dkv", (M, 2 * dm), BF16)
-            kv = a["kv"]
-            call("dig_dec_attention_bwd", a["qc"], dm, kv, 2 * dm, kv[:, dm:], 2 * dm, a["ca"], dm, dca, dm, a["lse_c"], None, dqc, dm,
-                 dkv, 2 * dm, dkv[:, dm:], 2 * dm, B, H, T, TOK, self.scale)
+            dattx = self._zero_once("b.dattx", (M, dm), BF16)          # rows >= T of every 256-row tile stay zero
+            dattx.view(B, TOK, dm)[:, :T].copy_(dca.view(B, T, dm))
+            dqkvx = Bf.get("b.dqkvx", (M, 3 * dm), BF16)
+            ops.attention_bwd(a["qkvx"], a["attx"], dattx, a["lse_c"], dqkvx, H, self.scale)
+            dqc.view(B, T, dm).copy_(dqkvx.view(B, TOK, 3 * dm)[:, :T, :dm])
+            dkv = dqkvx[:, dm:]
             wgrad(dqc, a["h2"], grads[p + "enc_attn.linear_q.weight"])
             wgrad(dkv, sv["mem"], self._pair_view(p + "enc_attn.linear_k.weight", p + "enc_attn.linear_v.weight"))
             ops.gemm(dkv, S_[p + "enc_kv"], dmem, b_mn_major=True, residual=None if first_mem else dmem)
@@ -397,6 +409,15 @@ class FinetuneStep(PretrainStep):
         self._encoder_bwd(sv["W"], sv["enc"], g, gb, grads)
         self.saved = None
         return [None if n == "encoder.mask_token" else grads[n] for n in self.train_names]
+
+    def _zero_once(self, name, shape, dtype):
+        """A buffer whose never-written part must read as zero: cleared when (re)allocated, not every step."""
+        t = self.bufs.d.get(name)
+        fresh = t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype
+        t = self.bufs.get(name, shape, dtype)
+        if fresh:
+            t.zero_()
+        return t
 
     def _pair_view(self, first, last):
         """One [rows, cols] fp32 view over the gradients of adjacent weights of equal width (they are consecutive in named_parameters
