@@ -186,12 +186,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 // other slot's softmax, which is the MUFU-bound critical resource.
 // ------------------------------------------------------------------------------------------------
 #ifndef DIG_ATTN_STAGGER
-#define DIG_ATTN_STAGGER 3000
+#define DIG_ATTN_STAGGER 2200
 #endif
 static constexpr long long kAttnStagger = DIG_ATTN_STAGGER;  // SM clocks between the first S products of slot 0 and slot 1
-static constexpr int kFwdPThreads = 320;
+static constexpr int kFwdPThreads = 352;  // warp 0: TMA, warps 1-2: MMA issue of slot 0 / 1, warps 3-10: softmax (two slots x 4 TMEM lane quarters)
 
-// Bring-up instrumentation: when a buffer is registered (dig_attention_debug_buffer), CTA 0 records SM clock stamps of its MMA thread
+// Bring-up instrumentation: when a buffer is registered (dig_attention_debug_buffer), CTA 0 records SM clock stamps of its MMA warps
 // and of one softmax thread per slot for the first 12 items (scripts/attn_timeline.py prints them).  Null in normal operation.
 __device__ long long* g_attn_dbg = nullptr;
 #define DIG_STAMP(role, n, k)                                                                         \
@@ -205,7 +205,45 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, a cubic minimax fit of
+// 2^f on [-0.5, 0.5] (max relative error 7.5e-5; the result is rounded to bf16, 2e-3), then n is added into the exponent field.
+// The softmax is MUFU-bound (16 ex2 per clock and SM against 64K scores per item); every DIG_ATTN_POLY-th score takes this path.
+#ifndef DIG_ATTN_POLY
+#define DIG_ATTN_POLY 0
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float fi = x + 12582912.0f;
+  const float f = x - (fi - 12582912.0f);
+  float p = fmaf(f, 0.055170830339193344f, 0.24260906875133514f);
+  p = fmaf(p, f, 0.693260908126831f);
+  p = fmaf(p, f, 0.9999281764030457f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(fi) << 23));
+}
+template <int E>
+__device__ __forceinline__ float ex2_sel(float x) {   // E = position of the score within its 32-column chunk (compile-time)
+  if constexpr (DIG_ATTN_POLY > 0 && (E % (DIG_ATTN_POLY > 0 ? DIG_ATTN_POLY : 1)) == (DIG_ATTN_POLY > 0 ? DIG_ATTN_POLY - 1 : 0)) return ex2_poly(x);
+  else return ex2_approx(x);
+}
 
+// exp2 of one 32-column chunk of scores: packed bf16 P for the PV product, fp32 row sums in two chains
+template <int J>
+__device__ __forceinline__ void exp_pair(const uint32_t (&v)[32], uint32_t (&pk)[16], float& sum0, float& sum1, float sl2, float mb) {
+  const float p0 = ex2_sel<J>(fmaf(__uint_as_float(v[J]), sl2, -mb));
+  const float p1 = ex2_sel<J + 1>(fmaf(__uint_as_float(v[J + 1]), sl2, -mb));
+  sum0 += p0;
+  sum1 += p1;
+  pk[J >> 1] = pack_bf16(p0, p1);
+  if constexpr (J + 2 < 32) exp_pair<J + 2>(v, pk, sum0, sum1, sl2, mb);
+}
+__device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], float& sum0, float& sum1, float sl2, float mb) {
+  exp_pair<0>(v, pk, sum0, sum1, sl2, mb);
+}
+
+// Slot layout in TMEM (256 columns per slot): S fp32 [128 q x 256 keys] fills all of it; the softmax overwrites it in place with
+//   cols   0- 63  P (bf16 pairs) of keys   0-127          cols  64-127  O accumulator (dead S columns once keys 0-127 are consumed)
+//   cols 128-191  P of keys 128-255                        cols 192-255  dead
+// so the PV product of the first key half is issued while the second half is still being exponentiated.
 __global__ void __launch_bounds__(kFwdPThreads, 1)
 attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
                         int heads, float scale, int num_items) {
@@ -213,20 +251,21 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFwdPBuf + 2 * 16384);   // after the two 16 KB output staging tiles
-  uint64_t* qk_full = bars + 0;    // [2 buffers] TMA -> MMA
-  uint64_t* v_full = bars + 2;     // [2 buffers] TMA -> MMA
-  uint64_t* v_empty = bars + 4;    // [2 buffers] MMA -> TMA: both PV products have read V
+  uint64_t* qk_full = bars + 0;    // [2 buffers] TMA -> MMA warps
+  uint64_t* v_full = bars + 2;     // [2 buffers] TMA -> MMA warps
+  uint64_t* v_empty = bars + 4;    // [2 buffers] MMA -> TMA (2 arrivals): both slots' PV products have read V
   uint64_t* s_full = bars + 6;     // [2 slots]   MMA -> softmax
-  uint64_t* p_full = bars + 8;     // [2 slots]   softmax -> MMA (128 arrivals)
-  uint64_t* o_full = bars + 10;    // [2 slots]   MMA -> softmax
-  uint64_t* s_free = bars + 12;    // [2 slots]   softmax -> MMA (128 arrivals): O drained, the slot's TMEM may be overwritten
-  uint64_t* k_empty = bars + 14;   // [2 buffers] MMA -> TMA: both S products have read K (released a softmax phase before V)
-  uint64_t* q_empty = bars + 16;   // [2 slots][2 buffers] MMA -> TMA: the slot's S product has read its Q tile
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* p_half = bars + 8;     // [2 slots][2 key halves] softmax -> MMA (128 arrivals)
+  uint64_t* o_full = bars + 12;    // [2 slots]   MMA -> softmax
+  uint64_t* s_free = bars + 14;    // [2 slots]   softmax -> MMA (128 arrivals): O is in registers, the slot's TMEM may be overwritten
+  uint64_t* k_empty = bars + 16;   // [2 buffers] MMA -> TMA (2 arrivals): both S products have read K (a softmax phase before V)
+  uint64_t* q_empty = bars + 18;   // [2 slots][2 buffers] MMA -> TMA: the slot's S product has read its Q tile
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
+  volatile long long* t_first = reinterpret_cast<volatile long long*>(bars + 23);   // clock of slot 0's first S issue (0 = not yet)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * kHd;
-  long long* const dbg = (blockIdx.x == 0 && (warp == 1 || (lane == 0 && (warp & 3) == 0))) ? g_attn_dbg : nullptr;
+  long long* const dbg = (blockIdx.x == 0 && (warp == 1 || warp == 2 || (lane == 0 && ((warp - 3) & 3) == 0))) ? g_attn_dbg : nullptr;
   if (dbg != nullptr && warp == 1 && lane == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -240,15 +279,17 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qk_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
+      mbar_init(&k_empty[i], 2);
       mbar_init(&q_empty[i], 1);
       mbar_init(&q_empty[2 + i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_half[2 * i], 128);
+      mbar_init(&p_half[2 * i + 1], 128);
       mbar_init(&o_full[i], 1);
       mbar_init(&s_free[i], 128);
     }
+    *t_first = 0;
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, 512);
@@ -256,7 +297,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_holder, 0);   // warp-uniform for the compiler too
-  constexpr uint32_t kColO = 192;
+  constexpr uint32_t kColO = 64, kColP1 = 128;
   pdl_wait();   // prologue done: the qkv tensor written by the preceding GEMM is read from here on
 
   if (warp == 0) {
@@ -283,78 +324,68 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tma_load_2d(base + 81920, &tm_qkv, &v_full[b], 2 * d + head * kHd, row0 + 128);
       }
     }
-  } else if (warp == 1) {
-    // Event-driven issue: each slot is its own S -> (softmax) -> PV pipeline.  The warp probes (mbarrier.test_wait, non-blocking; lane 0
-    // probes, a vote makes the result warp-uniform) the barriers the slot's next action needs and issues whichever is ready, and slot 1
-    // is started half a period late, so one slot's MMAs, O drain and barrier round trips hide behind the other slot's exp2 work instead
-    // of both slots hitting the MUFU pipe -- and then both leaving it -- together (clock stamps: 48 % MUFU duty in lock-step).
-    // The whole warp walks the loop and ONE ELECTED lane issues: with the loop inside `if (lane == 0)` ptxas wraps every tcgen05.mma in an
-    // ELECT / R2UR waterfall (~20 instructions), which held the PV products (16 x N=64) at 80 clocks per instruction.
+  } else if (warp <= 2) {
+    // One issuing warp per slot (blocking waits): each slot is its own S -> (softmax) -> PV pipeline and neither waits behind the
+    // other's 16-instruction PV issue (with one polling warp for both, clock stamps showed 600-900 clocks between a barrier completing
+    // and the MMAs it releases being issued).  Slot 1 is started half a period late, so one slot's MMAs, O drain and barrier round
+    // trips hide behind the other slot's exp2 work instead of both slots hitting the MUFU pipe -- and then both leaving it -- together.
+    // The whole warp walks the loop and ONE ELECTED lane issues (operands stay in uniform registers).
+    const int s = warp - 1;
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 256, false, false);
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
     const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t smem_s = smem_u32(smem);
-    int cnt0 = 0, cnt1 = 0;          // items completed (PV issued) per slot
-    int stage0 = 0, stage1 = 0;      // 0: S to issue, 1: PV to issue
-    int pv_issued0 = 0, pv_issued1 = 0;  // per buffer: slots whose PV of the buffer's current item has been issued
-    int s_issued0 = 0, s_issued1 = 0;    // per buffer: slots whose S of the buffer's current item has been issued
-    bool first_s0 = false;
-    long long t_first = 0;
-    while (cnt0 < my_items || cnt1 < my_items) {
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int n = s == 0 ? cnt0 : cnt1;
-        const int stg = s == 0 ? stage0 : stage1;
-        if (n >= my_items) continue;
-        const int b = n & 1;
-        const uint32_t u = (uint32_t)(n >> 1) & 1u, np = (uint32_t)n & 1u;
-        const uint32_t base = smem_s + b * kFwdPBuf;
-        bool ok = false;
-        if (lane == 0) {
-          if (stg == 0) {
-            ok = mbar_test_wait(&qk_full[b], u) && mbar_test_wait(&s_free[s], np ^ 1u);
-            if (s == 1 && n == 0) ok = ok && first_s0 && (clock64() - t_first >= kAttnStagger);   // slot 0 leads by half a period
-          } else {
-            ok = mbar_test_wait(&p_full[s], np) && mbar_test_wait(&v_full[b], u);
-          }
+    const uint32_t ts = tmem + (uint32_t)s * 256u;
+    for (int n = 0; n < my_items; ++n) {
+      const int b = n & 1;
+      const uint32_t u = (uint32_t)(n >> 1) & 1u, np = (uint32_t)n & 1u;
+      const uint32_t base = smem_s + b * kFwdPBuf;
+      mbar_wait(&qk_full[b], u);
+      mbar_wait(&s_free[s], np ^ 1u);
+      if (s == 1 && n == 0 && kAttnStagger > 0) {
+        long long t0;
+        while ((t0 = *t_first) == 0) {
         }
-        if (!__any_sync(0xffffffffu, ok)) continue;
-        tc_fence_after();
-        if (stg == 0) {
-          if (s == 0 && n == 0) { first_s0 = true; t_first = clock64(); }
-          const int si = (b == 0 ? s_issued0 : s_issued1) + 1;
-          if (elect_one()) {
-            DIG_STAMP(0, n, 1 + s);
-#pragma unroll
-            for (int k = 0; k < kHd / 16; ++k)
-              tc_mma_ss(tmem + s * 256, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024),
-                        make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s, k > 0);
-            tc_commit(&s_full[s]);
-            tc_commit(&q_empty[2 * s + b]);
-            if (si == 2) tc_commit(&k_empty[b]);
-          }
-          __syncwarp();
-          if (b == 0) s_issued0 = si == 2 ? 0 : si; else s_issued1 = si == 2 ? 0 : si;
-          if (s == 0) stage0 = 1; else stage1 = 1;
-        } else {
-          const int pv = (b == 0 ? pv_issued0 : pv_issued1) + 1;
-          if (elect_one()) {
-            DIG_STAMP(0, n, 4 + s);
-#pragma unroll
-            for (int k = 0; k < kTok / 16; ++k)
-              tc_mma_ts(tmem + s * 256 + kColO, tmem + s * 256 + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o,
-                        k > 0);
-            tc_commit(&o_full[s]);
-            if (pv == 2) tc_commit(&v_empty[b]);   // both slots are through with this item's V
-          }
-          __syncwarp();
-          if (b == 0) pv_issued0 = pv == 2 ? 0 : pv; else pv_issued1 = pv == 2 ? 0 : pv;
-          if (s == 0) { stage0 = 0; cnt0 = n + 1; } else { stage1 = 0; cnt1 = n + 1; }
+        while (clock64() - t0 < kAttnStagger) {
         }
       }
+      tc_fence_after();
+      if (elect_one()) {
+        DIG_STAMP(0, n, 1 + s);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          tc_mma_ss(ts, make_sdesc_sw128(base + s * 16384 + k * 32, 16, 1024), make_sdesc_sw128(base + 32768 + k * 32, 16, 1024), idesc_s,
+                    k > 0);
+        tc_commit(&s_full[s]);
+        tc_commit(&q_empty[2 * s + b]);
+        tc_commit(&k_empty[b]);
+        if (s == 0 && n == 0) *t_first = clock64() | 1;
+      }
+      __syncwarp();
+      mbar_wait(&v_full[b], u);
+      mbar_wait(&p_half[2 * s], np);
+      tc_fence_after();
+      if (elect_one()) {
+        DIG_STAMP(0, n, 4 + s);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          tc_mma_ts(ts + kColO, ts + k * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o, k > 0);
+      }
+      __syncwarp();
+      mbar_wait(&p_half[2 * s + 1], np);
+      tc_fence_after();
+      if (elect_one()) {
+        DIG_STAMP(0, n, 6 + s);
+#pragma unroll
+        for (int k = 8; k < 16; ++k)
+          tc_mma_ts(ts + kColO, ts + kColP1 + (k - 8) * 8, make_sdesc_sw128(base + 65536 + k * 2048, 8192, 1024), idesc_o, 1);
+        tc_commit(&o_full[s]);
+        tc_commit(&v_empty[b]);   // second arrival (either order): both slots are through with this item's V
+      }
+      __syncwarp();
     }
   } else {
-    const int s = (warp - 2) >> 2;
+    const int s = (warp - 3) >> 2;
     const int quarter = warp & 3;
     const int t = quarter * 32 + lane;  // query row within the slot's 128-row tile == TMEM lane
     const uint32_t tl = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * 256u;
@@ -368,9 +399,11 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       mbar_wait(&s_full[s], np);
       tc_fence_after();
       DIG_STAMP(1 + s, n, 1);
-      // both passes keep one TMEM load in flight behind the chunk being processed (two register buffers)
-      float mx = -INFINITY;
+      // both passes keep one TMEM load in flight behind the chunk being processed (two register buffers); the row maximum runs in
+      // four independent chains (one chain of 128 dependent FMNMX3 was ~900 clocks per row)
+      float mx;
       {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
         uint32_t va[32], vb[32];
         tmem_ld32(tl, va);
 #pragma unroll 1
@@ -378,12 +411,23 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           tmem_ld_wait();
           tmem_ld32(tl + c + 32, vb);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
+          for (int j = 0; j < 32; j += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(va[j + 0]), __uint_as_float(va[j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(va[j + 2]), __uint_as_float(va[j + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(va[j + 4]), __uint_as_float(va[j + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(va[j + 6]), __uint_as_float(va[j + 7])));
+          }
           tmem_ld_wait();
           if (c + 64 < kTok) tmem_ld32(tl + c + 64, va);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+          for (int j = 0; j < 32; j += 8) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(vb[j + 0]), __uint_as_float(vb[j + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(vb[j + 2]), __uint_as_float(vb[j + 3])));
+            m2 = fmaxf(m2, fmaxf(__uint_as_float(vb[j + 4]), __uint_as_float(vb[j + 5])));
+            m3 = fmaxf(m3, fmaxf(__uint_as_float(vb[j + 6]), __uint_as_float(vb[j + 7])));
+          }
         }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       const float mb = mx * sl2;
       DIG_STAMP(1 + s, n, 2);
@@ -393,36 +437,24 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tmem_ld32(tl, va);
 #pragma unroll 1
         for (int c = 0; c < kTok; c += 64) {
+          const uint32_t pc = tl + (uint32_t)(c >> 1) + (c >= 128 ? 64u : 0u);   // P columns of keys c..c+63
           uint32_t pk[16];
           tmem_ld_wait();
           tmem_ld32(tl + c + 32, vb);
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(va[j]), sl2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(va[j + 1]), sl2, -mb));
-            sum0 += p0;
-            sum1 += p1;
-            pk[j >> 1] = pack_bf16(p0, p1);
-          }
-          tmem_ld_wait();   // vb has landed: the S columns the next two P stores overwrite (c/2.., <= c+31) have been read
+          exp_chunk(va, pk, sum0, sum1, sl2, mb);
+          tmem_ld_wait();   // vb has landed: the S columns the next two P stores overwrite (<= c+31) have been read
           if (c + 64 < kTok) tmem_ld32(tl + c + 64, va);
-          tmem_st16(tl + (c >> 1), pk);
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[j]), sl2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[j + 1]), sl2, -mb));
-            sum0 += p0;
-            sum1 += p1;
-            pk[j >> 1] = pack_bf16(p0, p1);
+          tmem_st16(pc, pk);
+          exp_chunk(vb, pk, sum0, sum1, sl2, mb);
+          tmem_st16(pc + 16, pk);
+          if (c == 64 || c == 192) {   // a key half is complete (for c == 64 the load in flight reads columns 128-159: not touched by PV)
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_half[2 * s + (c >> 7)]);
+            DIG_STAMP(1 + s, n, 3 + (c >> 7));
           }
-          tmem_st16(tl + ((c + 32) >> 1), pk);
         }
       }
-      DIG_STAMP(1 + s, n, 3);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[s]);
-      DIG_STAMP(1 + s, n, 4);
 
       const float sum = sum0 + sum1;
       const float inv = 1.0f / sum;
@@ -430,29 +462,36 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       mbar_wait(&o_full[s], np);
       tc_fence_after();
       DIG_STAMP(1 + s, n, 5);
-      // O / sum goes out through a 128 x 64 bf16 swizzled staging tile and ONE TMA store per slot and item: a row-per-thread
-      // STG.128 touches 32 different lines per warp instruction (32 LSU wavefronts), which made the store the longest stall of the
-      // first version of this kernel.
-      if (t == 0) tma_store_wait_read_all();                 // last item's store has finished reading the staging tile
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
-#pragma unroll
-      for (int c = 0; c < kHd; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tl + kColO + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 p;
-          p.x = pack_bf16(__uint_as_float(v[j + 0]) * inv, __uint_as_float(v[j + 1]) * inv);
-          p.y = pack_bf16(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
-          p.z = pack_bf16(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
-          p.w = pack_bf16(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
-          sts_u4(stage_s + sw128_offset((uint32_t)t, (uint32_t)((c + j) >> 3)), p);
-        }
-      }
+      // O leaves TMEM in one go and the slot is handed back before the scaling / packing / staging work, so the next S product is
+      // issued ~300 clocks earlier.  O / sum goes out through a 128 x 64 bf16 swizzled staging tile and ONE TMA store per slot and
+      // item (a row-per-thread STG.128 touches 32 different lines per warp instruction).
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tl + kColO, o0);
+      tmem_ld32(tl + kColO + 32, o1);
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[s]);
       DIG_STAMP(1 + s, n, 6);
+      if (t == 0) tma_store_wait_read_all();                 // last item's store has finished reading the staging tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 p;
+        p.x = pack_bf16(__uint_as_float(o0[j + 0]) * inv, __uint_as_float(o0[j + 1]) * inv);
+        p.y = pack_bf16(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv);
+        p.z = pack_bf16(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv);
+        p.w = pack_bf16(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv);
+        sts_u4(stage_s + sw128_offset((uint32_t)t, (uint32_t)(j >> 3)), p);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 p;
+        p.x = pack_bf16(__uint_as_float(o1[j + 0]) * inv, __uint_as_float(o1[j + 1]) * inv);
+        p.y = pack_bf16(__uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv);
+        p.z = pack_bf16(__uint_as_float(o1[j + 4]) * inv, __uint_as_float(o1[j + 5]) * inv);
+        p.w = pack_bf16(__uint_as_float(o1[j + 6]) * inv, __uint_as_float(o1[j + 7]) * inv);
+        sts_u4(stage_s + sw128_offset((uint32_t)t, (uint32_t)((32 + j) >> 3)), p);
+      }
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory");
       if (t == 0) {

@@ -21,8 +21,8 @@ k = b[0, 11]
 print('CTA 0: %d clocks in %d ns -> %.3f GHz' % (k[1] - k[0], k[3] - k[2], float(k[1] - k[0]) / float(k[3] - k[2])))
 b[0, 11] = 0
 t0 = int(b[b > 0].min())
-names = ["MMA  : qk_full | s_free0 | s_free1 | S issued | p_full0 | p_full1 | PV issued",
-         "slot0: loop top | s_full | pass1 done | pass2 done | p arrive | o_full | s_free arrive | stored",
+names = ["MMA  : - | S issued slot0 | slot1 | - | PV(keys 0-127) issued slot0 | slot1 | PV(keys 128-255) issued slot0 | slot1",
+         "slot0: loop top | s_full | max pass done | P half 0 arrive | P half 1 arrive | o_full | s_free arrive (O in registers) | stored",
          "slot1: (same)"]
 for r in range(3):
     print(names[r])
