@@ -34,6 +34,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols);
 int make_tmap_2d(CUtensorMap* out, const void* base, int is_fp32, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                  uint32_t box_rows, uint32_t box_cols);
+// uint8 [rows, cols], box {64 bytes, box_rows}, 64-byte swizzle (8-bit GELU pre-activation codes)
+int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes, uint32_t box_rows);
 int num_sms();
 
 bool pdl_enabled();   // DIG_PDL (default on): launch with programmatic stream serialization
@@ -501,6 +503,11 @@ __device__ __forceinline__ void red_shared_add_f32(uint32_t a, float v) {
 __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {

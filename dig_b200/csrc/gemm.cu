@@ -12,6 +12,9 @@
 // modeling_pretrain_moco_mim_ori.py:463-482,422-426) and their autograd counterparts.
 #include <stdlib.h>
 
+#include <math.h>
+#include <mutex>
+
 #include "gemm_epilogue_tma.cuh"
 
 namespace dig {
@@ -28,7 +31,7 @@ struct GemmSmem {
   static constexpr int kStages = (BN == 128) ? (TMA_EPI ? 4 : 5) : 6;
   // epilogue scratch: one 32x32 fp32 transpose tile per warp (generic epilogue) or two 32 x 128 B TMA staging tiles per warp
   static constexpr int kEpi = TMA_EPI ? kEpiTmaBytes : kEpiWarps * 32 * 32 * 4;
-  static constexpr int kColsum = 2048 * 4;               // per-CTA column-sum scratch (N <= 2048 when colsum is requested)
+  static constexpr int kColsum = 2048 * 4 + 1024;        // per-CTA column-sum scratch (N <= 2048 when colsum is requested) + the 256-entry gelu' table (8-bit codes)
   static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
@@ -82,8 +85,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, kTmemCols);
-  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)
+  if (epi_is_gelu_bwd(MODE) && ep.colsum != nullptr)
     for (int i = threadIdx.x; i < N; i += kGemmThreads) cta_colsum[i] = 0.f;
+  if (epi_is_gelu_bwd(MODE) && epi_is_q8(MODE))   // constant table (written once at library initialisation): safe to read before pdl_wait
+    for (int i = threadIdx.x; i < 256; i += kGemmThreads) cta_colsum[2048 + i] = __ldg(ep.lut + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -194,7 +199,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)  // one global atomic per column per CTA
+  if (epi_is_gelu_bwd(MODE) && ep.colsum != nullptr)  // one global atomic per column per CTA
     for (int i = threadIdx.x; i < N; i += kGemmThreads) atomicAdd(ep.colsum + i, cta_colsum[i]);
   if (warp == 1) {
     tc_fence_after();
@@ -217,7 +222,8 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
   if (TMA_EPI) {
     rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
     if (rc) return rc;
-    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_ROWDOT) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    if (epi_is_q8(MODE)) rc = make_tmap_u8_2d(&tx, g->aux, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32);
+    else if ((epi_is_gelu(MODE) && g->aux != nullptr) || epi_is_gelu_bwd(MODE) || MODE == DIG_EPI_ROWDOT) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
     else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
     if (rc) return rc;
   }
@@ -230,11 +236,13 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
 
   GemmEpilogue ep;
   ep.out = g->out; ep.ldo = g->ldo;
-  ep.bias = g->bias ? g->bias : (MODE == DIG_EPI_GELU ? zero_bias() : nullptr); ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
+  ep.bias = g->bias ? g->bias : (epi_is_gelu(MODE) ? zero_bias() : nullptr); ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
   ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.colsum = g->colsum;
   ep.rowdot = g->rowdot; ep.ldrowdot = g->ldrowdot; ep.M = (int)g->M;
+  ep.lut = epi_is_q8(MODE) ? gelu_grad_lut() : nullptr;
+  if (epi_is_q8(MODE)) DIG_REQUIRE(ep.lut != nullptr, "dig_gemm: could not initialise the gelu' table");
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
   if (g->colsum) DIG_REQUIRE(g->epilogue == DIG_EPI_GELU_BWD && g->N <= 2048, "dig_gemm: colsum is built for DIG_EPI_GELU_BWD with N <= 2048 only");
 
@@ -255,7 +263,8 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
 template <int BN>
 static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0, f32 = g->out_fp32 != 0;
-  const int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+  int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+  if (g->aux_q8 && g->aux != nullptr) mode = (mode == DIG_EPI_GELU) ? kEpiGeluQ8 : kEpiGeluBwdQ8;
   const bool tma_ok = tma_epilogue_ok(g);
 #define DIG_CASE(A, B, MODE, F32) \
   if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm<BN, A, B, MODE, F32, false>(g, s);
@@ -267,9 +276,11 @@ static int dispatch(const dig_gemm_t* g, cudaStream_t s) {
   DIG_CASE_T(false, false, DIG_EPI_LINEAR, false)   // forward Linear -> bf16 (qkv, pix_decoder)
   DIG_CASE_T(false, false, DIG_EPI_LINEAR, true)    // forward Linear -> fp32 (+bias +residual, patch embed, BN-MLP heads)
   DIG_CASE_T(false, false, DIG_EPI_GELU, false)     // fc1 + GELU
+  DIG_CASE_T(false, false, kEpiGeluQ8, false)       // fc1 + GELU, pre-activation as 8-bit codes
   DIG_CASE_T(false, true, DIG_EPI_LINEAR, false)    // dgrad -> bf16
   DIG_CASE_T(false, true, DIG_EPI_LINEAR, true)     // dgrad -> fp32
   DIG_CASE_T(false, true, DIG_EPI_GELU_BWD, false)  // fc2 dgrad * gelu'
+  DIG_CASE_T(false, true, kEpiGeluBwdQ8, false)     // fc2 dgrad * gelu'(8-bit level)
   if (tma_ok) { DIG_CASE_T(false, true, DIG_EPI_ROWDOT, false) }   // proj dgrad + D = rowsum(dO o O) per head (TMA epilogue only)
   DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)  // BN-MLP dgrad through ReLU
   DIG_CASE_T(true, true, DIG_EPI_LINEAR, true)      // wgrad, single pass
@@ -294,6 +305,24 @@ const float* zero_bias() {
     void* a = nullptr;
     if (cudaGetSymbolAddress(&a, g_zero_bias) == cudaSuccess) p = reinterpret_cast<const float*>(a);
   }
+  return p;
+}
+
+// gelu_erf'(x) = Phi(x) + x phi(x) at the 256 code levels of dig_gemm_t.aux_q8 (computed in double, uploaded once)
+__device__ float g_gelu_grad_lut[256];
+const float* gelu_grad_lut() {
+  static const float* p = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    float h[256];
+    for (int i = 0; i < 256; ++i) {
+      const double x = (double)i * (2.0 * kQ8Range / 255.0) - (double)kQ8Range;
+      h[i] = (float)(0.5 * (1.0 + erf(x * 0.70710678118654752440)) + x * exp(-0.5 * x * x) * 0.39894228040143267794);
+    }
+    void* a = nullptr;
+    if (cudaMemcpyToSymbol(g_gelu_grad_lut, h, sizeof(h)) == cudaSuccess && cudaGetSymbolAddress(&a, g_gelu_grad_lut) == cudaSuccess)
+      p = reinterpret_cast<const float*>(a);
+  });
   return p;
 }
 
@@ -334,6 +363,9 @@ extern "C" int dig_gemm(const dig_gemm_t* g_in, void* stream) {
                 "dig_gemm: DIG_EPI_ROWDOT needs bf16 out, N %% 64 == 0 and rowdot[M, >= N/64]");
   if (g->epilogue != DIG_EPI_LINEAR && !(g->epilogue == DIG_EPI_GELU && g->aux == nullptr))   // GELU forward: the pre-activation copy is optional
     DIG_REQUIRE(g->aux != nullptr && g->ldaux % 4 == 0, "dig_gemm: epilogue %d needs aux", g->epilogue);
+  if (g->aux_q8)
+    DIG_REQUIRE((g->epilogue == DIG_EPI_GELU || g->epilogue == DIG_EPI_GELU_BWD) && g->aux != nullptr,
+                "dig_gemm: aux_q8 applies to the GELU / GELU' epilogues with an aux tensor only");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (use_2cta()) {
     const int r = gemm2_try(g, s);

@@ -26,7 +26,7 @@ struct Gemm2Smem {
   static constexpr int kStageB = (BN / 2) * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kEpi = TMA_EPI ? kEpiTmaBytes : kEpiWarps * 32 * 32 * 4;
-  static constexpr int kColsum = (MODE == DIG_EPI_GELU_BWD) ? 2048 * 4 : 0;   // per-CTA column-sum scratch: only the GELU' epilogue uses it
+  static constexpr int kColsum = (epi_is_gelu_bwd(MODE)) ? 2048 * 4 + 1024 : 0;   // per-CTA column-sum scratch + the 256-entry gelu' table (8-bit codes): only the GELU' epilogue uses them
   // as many ring stages as fit in 227 KB: the ring holds only ~1 us of MMA work and every tile's operands are first touched from DRAM
   static constexpr int kStages = (232448 - 1024 - 512 - kEpi - kColsum) / kStage > 6 ? 6 : (232448 - 1024 - 512 - kEpi - kColsum) / kStage;
   static constexpr int kBytes = kStages * kStage + kEpi + kColsum + 1024 + 512;
@@ -131,8 +131,10 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_holder, kTmemCols);
-  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)
+  if (epi_is_gelu_bwd(MODE) && ep.colsum != nullptr)
     for (int i = threadIdx.x; i < N; i += kGemm2Threads) cta_colsum[i] = 0.f;
+  if (epi_is_gelu_bwd(MODE) && epi_is_q8(MODE))   // constant table (written once at library initialisation): safe to read before pdl_wait
+    for (int i = threadIdx.x; i < 256; i += kGemm2Threads) cta_colsum[2048 + i] = __ldg(ep.lut + i);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // peer barriers are initialised before anyone arrives on them remotely
@@ -287,7 +289,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the pair leaves together: the leader's MMAs read the peer's shared memory, arrivals are remote
-  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr)
+  if (epi_is_gelu_bwd(MODE) && ep.colsum != nullptr)
     for (int i = threadIdx.x; i < N; i += kGemm2Threads) atomicAdd(ep.colsum + i, cta_colsum[i]);
   if (warp == 1) {
     tc_fence_after();
@@ -310,7 +312,8 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
   if (TMA_EPI) {
     rc = make_tmap_2d(&to, g->out, OUT_F32 ? 1 : 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldo, 32, OUT_F32 ? 32 : 64);
     if (rc) return rc;
-    if ((MODE == DIG_EPI_GELU && g->aux != nullptr) || MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_ROWDOT) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
+    if (epi_is_q8(MODE)) rc = make_tmap_u8_2d(&tx, g->aux, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32);
+    else if ((epi_is_gelu(MODE) && g->aux != nullptr) || epi_is_gelu_bwd(MODE) || MODE == DIG_EPI_ROWDOT) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
     else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
     if (rc) return rc;
   }
@@ -323,11 +326,13 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
 
   GemmEpilogue ep;
   ep.out = g->out; ep.ldo = g->ldo;
-  ep.bias = g->bias ? g->bias : (MODE == DIG_EPI_GELU ? zero_bias() : nullptr); ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
+  ep.bias = g->bias ? g->bias : (epi_is_gelu(MODE) ? zero_bias() : nullptr); ep.residual = g->residual; ep.ldr = g->ldr; ep.res_row_mod = g->res_row_mod;
   ep.row_mask = g->row_mask; ep.row_mask_value = g->row_mask_value;
   ep.aux = g->aux; ep.ldaux = g->ldaux; ep.alpha = g->alpha;
   ep.colsum = g->colsum;
   ep.rowdot = g->rowdot; ep.ldrowdot = g->ldrowdot; ep.M = (int)g->M;
+  ep.lut = epi_is_q8(MODE) ? gelu_grad_lut() : nullptr;
+  if (epi_is_q8(MODE)) DIG_REQUIRE(ep.lut != nullptr, "dig_gemm: could not initialise the gelu' table");
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DIG_GEMM_DBG"); dbg = e ? atoi(e) : 0; } ep.dbg = dbg; }
 
   auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, MODE, OUT_F32, TMA_EPI>;
@@ -347,7 +352,8 @@ static int launch_gemm2(const dig_gemm_t* g, cudaStream_t stream) {
 template <int BN>
 static int dispatch2(const dig_gemm_t* g, cudaStream_t s) {
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0, f32 = g->out_fp32 != 0;
-  const int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+  int mode = g->split_k > 1 ? kEpiAtomic : g->epilogue;
+  if (g->aux_q8 && g->aux != nullptr) mode = (mode == DIG_EPI_GELU) ? kEpiGeluQ8 : kEpiGeluBwdQ8;
   const bool tma_ok = tma_epilogue_ok(g);
 #define DIG_CASE(A, B, MODE, F32) \
   if (amn == A && bmn == B && mode == MODE && f32 == F32) return launch_gemm2<BN, A, B, MODE, F32, false>(g, s);
@@ -359,10 +365,12 @@ static int dispatch2(const dig_gemm_t* g, cudaStream_t s) {
   DIG_CASE_T(false, false, DIG_EPI_LINEAR, false)
   DIG_CASE_T(false, false, DIG_EPI_LINEAR, true)
   DIG_CASE_T(false, false, DIG_EPI_GELU, false)
+  DIG_CASE_T(false, false, kEpiGeluQ8, false)
   if constexpr (BN != 192) {  // MN-major B is staged in 64-column boxes: BN/2 must be a multiple of 64
     DIG_CASE_T(false, true, DIG_EPI_LINEAR, false)
     DIG_CASE_T(false, true, DIG_EPI_LINEAR, true)
     DIG_CASE_T(false, true, DIG_EPI_GELU_BWD, false)
+    DIG_CASE_T(false, true, kEpiGeluBwdQ8, false)
     if (tma_ok) { DIG_CASE_T(false, true, DIG_EPI_ROWDOT, false) }
     DIG_CASE(false, true, DIG_EPI_RELU_MASK, true)
     DIG_CASE_T(true, true, DIG_EPI_LINEAR, true)

@@ -14,6 +14,12 @@ namespace dig {
 
 static constexpr int kEpiWarps = 8;
 static constexpr int kEpiAtomic = 4;  // MODE value: split-K fp32 atomic accumulate
+// internal MODE values: the GELU epilogues with the pre-activation kept as 8-bit codes (dig_gemm_t.aux_q8) are separate instantiations,
+// so neither variant carries the other's code
+static constexpr int kEpiGeluQ8 = 6, kEpiGeluBwdQ8 = 7;
+__host__ __device__ constexpr bool epi_is_gelu(int m) { return m == DIG_EPI_GELU || m == kEpiGeluQ8; }
+__host__ __device__ constexpr bool epi_is_gelu_bwd(int m) { return m == DIG_EPI_GELU_BWD || m == kEpiGeluBwdQ8; }
+__host__ __device__ constexpr bool epi_is_q8(int m) { return m == kEpiGeluQ8 || m == kEpiGeluBwdQ8; }
 
 struct GemmEpilogue {
   void* out;
@@ -31,12 +37,32 @@ struct GemmEpilogue {
   float* rowdot;      // DIG_EPI_ROWDOT (TMA epilogue only)
   long long ldrowdot;
   int M;
+  const float* lut;   // aux_q8: device table [256] of gelu_erf'(decoded pre-activation)
   int dbg;  // bring-up only (env DIG_GEMM_DBG): 1 = skip the global stores, 2 = skip the whole epilogue body
 };
 
 // A device-resident zero vector standing in for a missing bias in the GELU epilogue (so that the bias add is unconditional there).
 const float* zero_bias();
 static constexpr int kZeroBiasLen = 8192;
+
+// 8-bit code of a GELU pre-activation (dig_gemm_t.aux_q8): 256 uniform levels over [-kQ8Range, kQ8Range].  The backward looks
+// gelu_erf'(level) up in a 256-entry table (exact values, computed in double on the host) instead of evaluating the rational.
+static constexpr float kQ8Range = 4.0f;
+const float* gelu_grad_lut();
+__device__ __forceinline__ uint32_t q8_bits(float x) {   // low byte = code; two FFMA (saturating scale, then the 2^23 rounding trick)
+  float t;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t) : "f"(x), "f"(0.5f / kQ8Range), "f"(0.5f));
+  return __float_as_uint(fmaf(t, 255.0f, 8388608.0f));
+}
+__device__ __forceinline__ uint32_t q8_encode4(float a, float b, float c, float d) {
+  return __byte_perm(__byte_perm(q8_bits(a), q8_bits(b), 0x0040), __byte_perm(q8_bits(c), q8_bits(d), 0x0040), 0x5410);
+}
+// table offset (bytes) of code k (0..3) of a packed word
+template <int K>
+__device__ __forceinline__ uint32_t q8_lut_off(uint32_t w) {
+  if constexpr (K == 0) return (w << 2) & 0x3FCu;
+  else return (w >> (8 * K - 2)) & 0x3FCu;
+}
 
 __device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
   const uint2 v = *reinterpret_cast<const uint2*>(p);
@@ -66,7 +92,9 @@ __device__ __forceinline__ void epi_prefetch(EpiPre<MODE>& p, const GemmEpilogue
         if (ep.residual != nullptr)
           p.v[i] = *reinterpret_cast<const float4*>(ep.residual + (ep.res_row_mod > 0 ? (grow % ep.res_row_mod) : grow) * ep.ldr + gcol);
         if (ep.row_mask != nullptr && ep.row_mask[grow] != 0) p.maskbits |= 1u << i;
-      } else if (MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_RELU_MASK) {
+      } else if (epi_is_gelu_bwd(MODE) && epi_is_q8(MODE)) {
+        p.v[i].x = __uint_as_float(*reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(ep.aux) + grow * ep.ldaux + gcol));
+      } else if (epi_is_gelu_bwd(MODE) || MODE == DIG_EPI_RELU_MASK) {
         const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(ep.aux) + grow * ep.ldaux + gcol);
         p.v[i].x = __uint_as_float(t.x);
         p.v[i].y = __uint_as_float(t.y);
@@ -107,14 +135,23 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const EpiPre<
         continue;
       }
       f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-      if (MODE == DIG_EPI_GELU) {
-        if (ep.aux != nullptr) st_bf16x4(reinterpret_cast<__nv_bfloat16*>(ep.aux) + grow * ep.ldaux + gcol, f);
+      if (epi_is_gelu(MODE)) {
+        if (ep.aux != nullptr) {
+          if (epi_is_q8(MODE)) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ep.aux) + grow * ep.ldaux + gcol) = q8_encode4(f.x, f.y, f.z, f.w);
+          else st_bf16x4(reinterpret_cast<__nv_bfloat16*>(ep.aux) + grow * ep.ldaux + gcol, f);
+        }
         f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); f.z = gelu_erf(f.z); f.w = gelu_erf(f.w);
-      } else if (MODE == DIG_EPI_GELU_BWD || MODE == DIG_EPI_RELU_MASK) {
+      } else if (epi_is_gelu_bwd(MODE) || MODE == DIG_EPI_RELU_MASK) {
         const uint32_t lo = __float_as_uint(pre.v[i].x), hi = __float_as_uint(pre.v[i].y);
         const float4 x = make_float4(bf16_lo(lo), bf16_hi(lo), bf16_lo(hi), bf16_hi(hi));
-        if (MODE == DIG_EPI_GELU_BWD) {
-          f.x *= gelu_erf_grad(x.x); f.y *= gelu_erf_grad(x.y); f.z *= gelu_erf_grad(x.z); f.w *= gelu_erf_grad(x.w);
+        if (epi_is_gelu_bwd(MODE)) {
+          if (epi_is_q8(MODE)) {
+            const char* lut = reinterpret_cast<const char*>(ep.lut);
+            f.x *= __ldg(reinterpret_cast<const float*>(lut + q8_lut_off<0>(lo))); f.y *= __ldg(reinterpret_cast<const float*>(lut + q8_lut_off<1>(lo)));
+            f.z *= __ldg(reinterpret_cast<const float*>(lut + q8_lut_off<2>(lo))); f.w *= __ldg(reinterpret_cast<const float*>(lut + q8_lut_off<3>(lo)));
+          } else {
+            f.x *= gelu_erf_grad(x.x); f.y *= gelu_erf_grad(x.y); f.z *= gelu_erf_grad(x.z); f.w *= gelu_erf_grad(x.w);
+          }
           cs.x += f.x; cs.y += f.y; cs.z += f.z; cs.w += f.w;
         } else {
           f.x = x.x > 0.f ? f.x : 0.f; f.y = x.y > 0.f ? f.y : 0.f; f.z = x.z > 0.f ? f.z : 0.f; f.w = x.w > 0.f ? f.w : 0.f;
@@ -128,7 +165,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const EpiPre<
       else st_bf16x4(out_h + grow * ep.ldo + gcol, f);
     }
   }
-  if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr) {  // column sums of the written tile: bias gradient of fc1
+  if (epi_is_gelu_bwd(MODE) && ep.colsum != nullptr) {  // column sums of the written tile: bias gradient of fc1
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
       cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);

@@ -47,20 +47,27 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
   constexpr int G = OUT_F32 ? 32 : 64;            // columns per 128-byte staging row
   constexpr int NGT = (BNT + G - 1) / G;          // column groups in the tile
   static_assert(BNT % G == 0, "tile width must be a multiple of the staging group");
-  const bool has_ld = (MODE == DIG_EPI_GELU_BWD) || (MODE == DIG_EPI_ROWDOT) || (MODE == DIG_EPI_LINEAR && OUT_F32 && ep.residual != nullptr);
+  const bool has_ld = (epi_is_gelu_bwd(MODE)) || (MODE == DIG_EPI_ROWDOT) || (MODE == DIG_EPI_LINEAR && OUT_F32 && ep.residual != nullptr);
   const bool has_bias = ep.bias != nullptr;
   const uint32_t row_s = (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7);
+  // 8-bit pre-activation codes (dig_gemm_t.aux_q8): the aux tile is 32 rows x 64 B in a 64-byte-swizzled staging tile (16-byte chunk c
+  // of row r at r*64 + ((c ^ ((r >> 1) & 3)) << 4)), a quarter of the bf16 tile's bytes; the backward multiplies by a 256-entry table of
+  // gelu' held in shared memory (behind the CTA's column-sum scratch) instead of evaluating the rational.
+  constexpr bool q8 = epi_is_q8(MODE);
+  const uint32_t q8_row = (uint32_t)lane * 64u, q8_sw = ((uint32_t)lane >> 1) & 3u;
+  const uint32_t lut_s = smem_u32(cta_colsum) + 2048u * 4u;
+  const uint32_t ld_bytes = (epi_is_gelu_bwd(MODE) && q8) ? kStageTileBytes / 2 : kStageTileBytes;
 
   // first group's operand load, before the accumulator wait
   if (lane == 0) tma_store_wait_read_all();       // staging tiles of the previous output tile are free again
   __syncwarp();
   if (has_ld && half < NGT && lane == 0) {
-    mbar_expect_tx(&st.ld_bar[0], kStageTileBytes);
+    mbar_expect_tx(&st.ld_bar[0], ld_bytes);
     tma_load_2d_addr(st.stage_s, tm_aux, &st.ld_bar[0], n0 + half * G, row_base);
 #if DIG_EPI_EARLY_LD
     if (half + 2 < NGT) {   // the second group's operand as well: both staging tiles are free here, and the load then has the accumulator
-      mbar_expect_tx(&st.ld_bar[1], kStageTileBytes);   // wait plus one whole group of math to arrive (it waited ~15 % of the epilogue's time)
+      mbar_expect_tx(&st.ld_bar[1], ld_bytes);   // wait plus one whole group of math to arrive (it waited ~15 % of the epilogue's time)
       tma_load_2d_addr(st.stage_s + kStageTileBytes, tm_aux, &st.ld_bar[1], n0 + (half + 2) * G, row_base);
     }
 #endif
@@ -80,12 +87,12 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
     if (gi >= NGT) break;
     const bool last = (gi + 2 >= NGT);
     const int gcol = n0 + gi * G;
-    const uint32_t buf = st.stage_s + (uint32_t)((MODE == DIG_EPI_GELU) ? 0 : (k & 1)) * kStageTileBytes;
+    const uint32_t buf = st.stage_s + (uint32_t)((epi_is_gelu(MODE)) ? 0 : (k & 1)) * kStageTileBytes;
     const uint32_t buf2 = st.stage_s + kStageTileBytes;   // GELU forward: second output (post-activation)
     constexpr int kFirstPrefetch = DIG_EPI_EARLY_LD ? 1 : 0;   // group k prefetches group k+1 unless the tile start already requested it
     if (k > 0 && (!has_ld || (!last && k >= kFirstPrefetch))) {  // the staging tile we are about to overwrite (or prefetch into) must have been read by its TMA store
       if (lane == 0) {
-        if (has_ld || MODE == DIG_EPI_GELU) tma_store_wait_read_all();
+        if (has_ld || epi_is_gelu(MODE)) tma_store_wait_read_all();
         else tma_store_wait_read_1();      // double-buffered: only the store issued two groups ago has to be done
       }
       __syncwarp();
@@ -93,7 +100,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
     if (has_ld) {
       if (!last && k >= kFirstPrefetch && lane == 0) {  // prefetch the next group's operand into the other staging tile
         uint64_t* nb = &st.ld_bar[(k + 1) & 1];
-        mbar_expect_tx(nb, kStageTileBytes);
+        mbar_expect_tx(nb, ld_bytes);
         tma_load_2d_addr(st.stage_s + (uint32_t)((k + 1) & 1) * kStageTileBytes, tm_aux, nb, gcol + 2 * G, row_base);
       }
       if (k & 1) { mbar_wait(&st.ld_bar[1], st.uses1 & 1); ++st.uses1; }
@@ -115,6 +122,16 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
       __syncwarp();
       release();
     }
+    uint32_t cw[16];   // GELU backward with 8-bit codes: this row's 64 codes, read before any lane overwrites the tile with its output row
+    if (epi_is_gelu_bwd(MODE) && q8) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 t = lds_u4(buf + q8_row + ((((uint32_t)c) ^ q8_sw) << 4));
+        cw[4 * c] = t.x; cw[4 * c + 1] = t.y; cw[4 * c + 2] = t.z; cw[4 * c + 3] = t.w;
+      }
+      __syncwarp();
+    }
+    uint2 qheld = make_uint2(0u, 0u);   // GELU forward with 8-bit codes: the even unit's 8 codes, stored together with the odd unit's
     const float alpha = ep.alpha;
     if (OUT_F32) {
       // 8 units of 4 fp32 columns
@@ -152,7 +169,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
         // GELU forward: the host always supplies a bias (a zero vector if the caller passed none), so the loads sit in the same basic
         // block as the polynomial and ptxas hoists them ahead of it; other modes: uniform branch on the kernel parameter.  Columns past
         // N are clipped by the TMA store, so their bias address is only clamped.
-        if (MODE == DIG_EPI_GELU || has_bias) {
+        if (epi_is_gelu(MODE) || has_bias) {
           const int bc = min(gcol + 8 * j, N - 8);
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + bc));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + bc + 4));
@@ -162,9 +179,16 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
           f2_unpack(f2_add(f2_pack(f[6], f[7]), f2_pack(b1.z, b1.w)), f[6], f[7]);
         }
         const uint32_t off = row_s + (((uint32_t)j ^ sw) << 4);
-        if (MODE == DIG_EPI_GELU) {
-          if (ep.aux != nullptr)   // pre-activation copy for the backward; the no-grad momentum branch skips it (half the stores)
-            sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+        if (epi_is_gelu(MODE)) {
+          if (ep.aux != nullptr) {   // pre-activation copy for the backward; the no-grad momentum branch skips it (half the stores)
+            if (q8) {
+              const uint2 cur = make_uint2(q8_encode4(f[0], f[1], f[2], f[3]), q8_encode4(f[4], f[5], f[6], f[7]));
+              if (j & 1) sts_u4(buf + q8_row + ((((uint32_t)(j >> 1)) ^ q8_sw) << 4), make_uint4(qheld.x, qheld.y, cur.x, cur.y));
+              else qheld = cur;
+            } else {
+              sts_u4(buf + off, make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+            }
+          }
 #if DIG_GELU_PACKED
 #pragma unroll
           for (int e = 0; e < 8; e += 2) gelu_erf_x2(f[e], f[e + 1], f[e], f[e + 1]);
@@ -179,7 +203,13 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
             dot += f[0] * bf16_lo(x.x) + f[1] * bf16_hi(x.x) + f[2] * bf16_lo(x.y) + f[3] * bf16_hi(x.y) + f[4] * bf16_lo(x.z) +
                    f[5] * bf16_hi(x.z) + f[6] * bf16_lo(x.w) + f[7] * bf16_hi(x.w);
           }
-          if (MODE == DIG_EPI_GELU_BWD) {
+          if (epi_is_gelu_bwd(MODE) && q8) {
+            const uint32_t w0 = cw[2 * j], w1 = cw[2 * j + 1];
+            f[0] *= lds_f32(lut_s + q8_lut_off<0>(w0)); f[1] *= lds_f32(lut_s + q8_lut_off<1>(w0));
+            f[2] *= lds_f32(lut_s + q8_lut_off<2>(w0)); f[3] *= lds_f32(lut_s + q8_lut_off<3>(w0));
+            f[4] *= lds_f32(lut_s + q8_lut_off<0>(w1)); f[5] *= lds_f32(lut_s + q8_lut_off<1>(w1));
+            f[6] *= lds_f32(lut_s + q8_lut_off<2>(w1)); f[7] *= lds_f32(lut_s + q8_lut_off<3>(w1));
+          } else if (epi_is_gelu_bwd(MODE)) {
             const uint4 x = lds_u4(buf + off);
 #if DIG_GELU_PACKED
             gelu_erf_grad_mul_x2(bf16_lo(x.x), bf16_hi(x.x), f[0], f[1]);
@@ -200,7 +230,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
         if (row_base + lane < ep.M && gcol < N) ep.rowdot[(long long)(row_base + lane) * ep.ldrowdot + (gcol >> 6)] = dot;
       }
     }
-    if (MODE == DIG_EPI_GELU_BWD && ep.colsum != nullptr) {
+    if (epi_is_gelu_bwd(MODE) && ep.colsum != nullptr) {
       // column sums of the staged 32 x 64 bf16 tile: lane l owns columns 2l, 2l+1 (bias gradient of fc1)
       __syncwarp();
       float s0 = 0.f, s1 = 0.f;   // rows past M are exact zeros (zero-filled A rows), so they need no masking
@@ -221,7 +251,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
     __syncwarp();
     if (lane == 0) {
       if (MODE == kEpiAtomic) tma_reduce_add_2d(tm_out, buf, gcol, row_base);
-      else if (MODE == DIG_EPI_GELU) {
+      else if (epi_is_gelu(MODE)) {
         if (ep.aux != nullptr) tma_store_2d(tm_aux, buf, gcol, row_base);   // pre-activation
         tma_store_2d(tm_out, buf2, gcol, row_base);  // gelu(pre)
       } else tma_store_2d(tm_out, buf, gcol, row_base);
@@ -241,7 +271,8 @@ static inline bool tma_epilogue_ok(const dig_gemm_t* g) {
   if (g->epilogue == DIG_EPI_RELU_MASK) return false;
   if ((g->N * es) % 16 || (g->ldo * es) % 16 || ((uintptr_t)g->out & 15)) return false;
   if (g->epilogue == DIG_EPI_GELU || g->epilogue == DIG_EPI_GELU_BWD || g->epilogue == DIG_EPI_ROWDOT) {
-    if (g->out_fp32 || (g->ldaux * 2) % 16 || ((uintptr_t)g->aux & 15)) return false;
+    const int aes = (g->aux_q8 && g->epilogue != DIG_EPI_ROWDOT) ? 1 : 2;
+    if (g->out_fp32 || (g->ldaux * aes) % 16 || ((uintptr_t)g->aux & 15)) return false;
   }
   if (g->epilogue == DIG_EPI_ROWDOT && (g->N % 64 != 0 || g->rowdot == nullptr)) return false;
   if (g->residual && (!g->out_fp32 || g->epilogue != DIG_EPI_LINEAR || (g->ldr * 4) % 16 || ((uintptr_t)g->residual & 15))) return false;

@@ -70,6 +70,20 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int is_fp32, uint64_t rows,
   return 0;
 }
 
+int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  DIG_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (u8) failed (%d) rows=%llu cols=%llu stride=%llu box=%u base=%p", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)row_stride_bytes, box_rows, base);
+  return 0;
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -90,7 +104,7 @@ int num_sms() {
 
 }  // namespace dig
 
-extern "C" int dig_version(void) { return 2; }
+extern "C" int dig_version(void) { return 3; }
 
 extern "C" int dig_sm(void) {
   int dev = 0, major = 0, minor = 0;

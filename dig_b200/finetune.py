@@ -147,6 +147,7 @@ class FinetuneStep(PretrainStep):
         self._side = torch.cuda.Stream(device=self.device) if self._two_streams else None
         self._always_cast = os.environ.get("DIG_ALWAYS_CAST", "0") == "1"
         self._bf16_grad_stream = os.environ.get("DIG_BF16_GRAD_STREAM", "1") != "0"
+        self._gelu_q8 = os.environ.get("DIG_GELU_Q8", "1") != "0"     # encoder + decoder FFN pre-activations as 8-bit codes (dig_gemm_t.aux_q8)
         self._sync_flat, self._sync_works, self._sync_group = None, [], None
         self._build()
 
@@ -290,7 +291,7 @@ class FinetuneStep(PretrainStep):
             m3, r3 = Bf.get(t + "m3", (Md,), F32), Bf.get(t + "r3", (Md,), F32)
             self._ln(x2, N_[p + "norm3.weight"], N_[p + "norm3.bias"], h3, m3, r3, eps=eps)
             di = S_[p + "mlp.w_1.weight"].shape[0]
-            fpre, f1 = Bf.get(t + "fpre", (Md, di), BF16), Bf.get(t + "f1", (Md, di), BF16)
+            fpre, f1 = Bf.get(t + "fpre", (Md, di), torch.uint8 if self._gelu_q8 else BF16), Bf.get(t + "f1", (Md, di), BF16)
             ops.gemm(h3, S_[p + "mlp.w_1.weight"], f1, bias=N_[p + "mlp.w_1.bias"], epilogue=ops.EPI_GELU, aux=fpre)
             x3 = Bf.get(t + "x3", (Md, dm), F32)
             ops.gemm(f1, S_[p + "mlp.w_2.weight"], x3, bias=N_[p + "mlp.w_2.bias"], residual=x2)

@@ -38,6 +38,7 @@ class _Gemm(ctypes.Structure):
         ("split_k", ctypes.c_int32),
         ("colsum", ctypes.c_void_p),
         ("rowdot", ctypes.c_void_p), ("ldrowdot", ctypes.c_int64),
+        ("aux_q8", ctypes.c_int32),
     ]
 
 
@@ -213,7 +214,13 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
         g.row_mask, g.row_mask_value = row_mask.data_ptr(), row_mask_value.data_ptr()
     g.epilogue = epilogue
     if aux is not None:
-        _req(aux, torch.bfloat16, "aux")
+        if aux.dtype == torch.uint8:        # 8-bit GELU pre-activation codes (dig_gemm_t.aux_q8)
+            if epilogue not in (EPI_GELU, EPI_GELU_BWD):
+                raise DigError("a uint8 aux tensor (8-bit pre-activation codes) is for the GELU / GELU' epilogues only")
+            _req(aux, torch.uint8, "aux")
+            g.aux_q8 = 1
+        else:
+            _req(aux, torch.bfloat16, "aux")
         g.aux, g.ldaux = aux.data_ptr(), aux.stride(0)
     g.alpha = alpha
     g.split_k = split_k
@@ -235,7 +242,7 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, residual=N
         if residual is not None:
             nbytes += 4.0 * M * N
         if aux is not None:
-            nbytes += 2.0 * M * N
+            nbytes += float(aux.element_size()) * M * N
         _gemm_prof.append((e0, e1, 2.0 * M * N * K, nbytes))
     else:
         _check(load().dig_gemm(ctypes.byref(g), _stream()), "dig_gemm")

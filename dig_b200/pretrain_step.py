@@ -128,6 +128,9 @@ class PretrainStep:
         # The running gradient of the residual stream through the encoder backward is a bf16 stream (each LayerNorm backward reads it and
         # writes the next one; it is the dgrad GEMM operand anyway) -- DIG_BF16_GRAD_STREAM=0 keeps the fp32 copy alongside (round 1).
         self._bf16_grad_stream = os.environ.get("DIG_BF16_GRAD_STREAM", "1") != "0"
+        # The GELU pre-activation is kept for the backward as 8-bit codes (include/dig_b200.h, dig_gemm_t.aux_q8): 100 instead of 200 MB
+        # written by fc1 and read by the GELU' dgrad per block -- DIG_GELU_Q8=0 keeps the bf16 copy (round 1).
+        self._gelu_q8 = os.environ.get("DIG_GELU_Q8", "1") != "0"
         self._side = torch.cuda.Stream(device=self.device) if self._two_streams else None
 
     # ------------------------------------------------------------------ parameter bookkeeping
@@ -263,7 +266,7 @@ class PretrainStep:
             ln2 = B.get(t + "ln2", (M, d), BF16)
             mean2, rstd2 = B.get(t + "m2", (M,), F32), B.get(t + "r2", (M,), F32)
             self._ln(xm, bw["n2w"], bw["n2b"], ln2, mean2, rstd2)
-            hpre = B.get(t + "hpre", (M, 4 * d), BF16) if save else None     # GELU pre-activation: only the backward reads it
+            hpre = B.get(t + "hpre", (M, 4 * d), torch.uint8 if self._gelu_q8 else BF16) if save else None     # GELU pre-activation: only the backward reads it
             hpost = B.get(t + "hpost", (M, 4 * d), BF16)
             ops.gemm(ln2, bw["f1w"], hpost, bias=bw["f1b"], epilogue=ops.EPI_GELU, aux=hpre)
             xn = B.get((tag + "x%d" % (l + 1)) if save else (tag + "x%d" % ((l + 1) % 2 + 1)), (M, d), F32)

@@ -32,8 +32,9 @@ const char* dig_last_error(void); /* thread-local message of the last failing ca
  * B stored [K,N]); leading dimensions are in elements and must be multiples of 8.               */
 enum {
   DIG_EPI_LINEAR = 0,   /* v = alpha*acc (+bias[n]) (row-masked replace) (+residual)                       */
-  DIG_EPI_GELU = 1,     /* pre = alpha*acc + bias ; aux[m,n] (bf16) = pre if aux != NULL ; v = gelu_erf(pre) (F:54-55) */
-  DIG_EPI_GELU_BWD = 2, /* v = alpha*acc * gelu_erf'(aux[m,n])  (aux: bf16 pre-activation)                 */
+  DIG_EPI_GELU = 1,     /* pre = alpha*acc + bias ; aux[m,n] = pre if aux != NULL ; v = gelu_erf(pre) (F:54-55)
+                           aux is bf16, or, with aux_q8 != 0, the 8-bit code of pre (see dig_gemm_t.aux_q8)            */
+  DIG_EPI_GELU_BWD = 2, /* v = alpha*acc * gelu_erf'(aux[m,n])  (aux: bf16 pre-activation, or its 8-bit code)       */
   DIG_EPI_RELU_MASK = 3,/* v = aux[m,n] > 0 ? alpha*acc : 0     (aux: bf16 post-ReLU activation)           */
   DIG_EPI_ROWDOT = 5    /* v = alpha*acc + bias (bf16 out) ; rowdot[m, n/64] = sum over the 64-column group of v * aux[m,n]
                            (aux: bf16 [M,N]).  Output-projection dgrad: v = dO, aux = O, rowdot = D of the attention backward */
@@ -57,6 +58,11 @@ typedef struct dig_gemm {
   float* colsum;                                   /* optional fp32 [N]: colsum[n] += sum_m out[m,n] (bias gradient of the layer
                                                       that produced the GEMM input), NULL to skip                        */
   float* rowdot; int64_t ldrowdot;                 /* DIG_EPI_ROWDOT: fp32 [M, ldrowdot >= N/64]                            */
+  int32_t aux_q8;                                  /* DIG_EPI_GELU / DIG_EPI_GELU_BWD: aux is uint8 [M, ldaux] holding
+                                                      code = round((clamp(pre, -4, 4) + 4) * 255 / 8) instead of bf16 pre: the
+                                                      backward only needs gelu_erf'(pre), a smooth function of pre (|slope| <=
+                                                      0.8), so 256 levels of 0.031 reproduce it to <= 1.3e-2 (3.6e-3 rms) with a
+                                                      quarter of the bytes of a bf16 copy written and read (ABI v3)           */
 } dig_gemm_t;
 int dig_gemm(const dig_gemm_t* g, void* stream);
 

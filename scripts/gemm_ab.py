@@ -21,19 +21,20 @@ f32 = lambda *s: torch.randn(*s, device="cuda")
 def split_k(m, n, k, bn=128):
     tiles = ((m + 127) // 128) * ((n + bn - 1) // bn); kb = (k + 63) // 64
     return max(1, min(kb, 148 // max(tiles, 1)))
-def fwd(N, K, out_f32, res, epi=ops.EPI_LINEAR, with_aux=True):
+def fwd(N, K, out_f32, res, epi=ops.EPI_LINEAR, with_aux=True, q8=False):
     def mk():
         a, w, b = bf(M, K), bf(N, K), f32(N)
         out = torch.empty(M, N, device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
         r = f32(M, N) if res else None
-        aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if (epi != ops.EPI_LINEAR and with_aux) else None
+        aux = torch.empty(M, N, device="cuda", dtype=torch.uint8 if q8 else torch.bfloat16) if (epi != ops.EPI_LINEAR and with_aux) else None
         return lambda: ops.gemm(a, w, out, bias=b, residual=r, epilogue=epi, aux=aux)
     return mk
-def dgrad(N, K, epi=ops.EPI_LINEAR, colsum=False):
+def dgrad(N, K, epi=ops.EPI_LINEAR, colsum=False, q8=False):
     def mk():
         a, w = bf(M, K), bf(K, N)
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         aux = bf(M, N) if epi != ops.EPI_LINEAR else None
+        if q8: aux = torch.randint(0, 256, (M, N), device="cuda", dtype=torch.uint8)
         cs = torch.zeros(N, device="cuda") if colsum else None
         return lambda: ops.gemm(a, w, out, b_mn_major=True, epilogue=epi, aux=aux, colsum=cs)
     return mk
@@ -48,10 +49,12 @@ fl = lambda n, k: 2.0 * M * n * k
 bench("qkv fwd 1152x384 bf16", fwd(3 * d, d, False, False), fl(3 * d, d))
 bench("proj fwd 384x384 f32+res", fwd(d, d, True, True), fl(d, d))
 bench("fc1 fwd GELU 1536x384", fwd(4 * d, d, False, False, ops.EPI_GELU), fl(4 * d, d))
+bench("fc1 fwd GELU 1536x384 q8 aux", fwd(4 * d, d, False, False, ops.EPI_GELU, True, True), fl(4 * d, d))
 bench("fc1 fwd GELU no-aux (momentum)", fwd(4 * d, d, False, False, ops.EPI_GELU, False), fl(4 * d, d))
 bench("fc1 fwd plain 1536x384 bf16", fwd(4 * d, d, False, False), fl(4 * d, d))
 bench("fc2 fwd 384x1536 f32+res", fwd(d, 4 * d, True, True), fl(d, 4 * d))
 bench("fc2 dgrad GELU_BWD+colsum", dgrad(4 * d, d, ops.EPI_GELU_BWD, True), fl(4 * d, d))
+bench("fc2 dgrad GELU_BWD+colsum q8 aux", dgrad(4 * d, d, ops.EPI_GELU_BWD, True, True), fl(4 * d, d))
 bench("fc2 dgrad GELU_BWD no-colsum", dgrad(4 * d, d, ops.EPI_GELU_BWD, False), fl(4 * d, d))
 bench("fc2 dgrad plain (N=1536,K=384)", dgrad(4 * d, d), fl(4 * d, d))
 bench("fc1 dgrad (N=384,K=1536)", dgrad(d, 4 * d), fl(d, 4 * d))

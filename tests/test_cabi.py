@@ -37,7 +37,7 @@ def test_library_links_no_driver(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.dig_version() == 2
+    assert lib.dig_version() == 3
     assert isinstance(lib.dig_last_error(), bytes)
 
 

@@ -94,6 +94,28 @@ def test_gelu_forward_and_backward_epilogues_at_65536_rows(ops):
     assert torch.allclose(cs, ref.sum(0), atol=3.0, rtol=5e-3)
 
 
+def test_gelu_epilogues_with_8bit_codes_at_65536_rows(ops):
+    """The same two kernels with the pre-activation kept as 8-bit codes (dig_gemm_t.aux_q8, what the step uses): 2-CTA kernel, TMA
+    epilogue, 64-byte-swizzled code tiles, gelu' from the shared-memory table."""
+    from tests.test_gpu_kernels import q8_codes, q8_gelu_grad
+    torch.manual_seed(13)
+    a, w1, b1 = rnd(MTOK, 384, dtype=torch.bfloat16), rnd(1536, 384, scale=0.1, dtype=torch.bfloat16), rnd(1536, scale=0.1)
+    post = torch.empty(MTOK, 1536, device="cuda", dtype=torch.bfloat16)
+    codes = torch.zeros(MTOK, 1536, device="cuda", dtype=torch.uint8)
+    ops.gemm(a, w1, post, bias=b1, epilogue=ops.EPI_GELU, aux=codes)
+    acc = a.float() @ w1.float().t() + b1
+    _close(post, torch.nn.functional.gelu(acc), 1e-2, 8e-3, "fc1 gelu")
+    diff = (codes.int() - q8_codes(acc).int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 2e-3
+    del acc, diff
+    dy, w2 = rnd(MTOK, 384, dtype=torch.bfloat16), rnd(384, 1536, scale=0.05, dtype=torch.bfloat16)
+    dh, cs = torch.empty(MTOK, 1536, device="cuda", dtype=torch.bfloat16), torch.zeros(1536, device="cuda")
+    ops.gemm(dy, w2, dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=codes, colsum=cs)
+    ref = (dy.float() @ w2.float()) * q8_gelu_grad(codes)
+    _close(dh, ref, 1e-2, 1e-2, "fc2 dgrad x gelu'(8-bit level)")
+    assert torch.allclose(cs, dh.float().sum(0), atol=0.5, rtol=1e-3)
+
+
 @pytest.mark.parametrize("N,K", [(384, 1536), (384, 1152)])
 def test_dgrad_bf16_at_65536_rows(ops, N, K):
     """gemm2<128,K-major,MN-major,LINEAR,bf16,TMA>: fc1 / qkv dgrad."""

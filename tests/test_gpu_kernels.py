@@ -104,6 +104,44 @@ def test_gemm_fused_epilogues(ops):
     assert torch.allclose(out, ref, atol=2e-4)
 
 
+def q8_codes(pre):
+    """The 8-bit pre-activation code of include/dig_b200.h (dig_gemm_t.aux_q8), restated with torch ops."""
+    return torch.round((pre.clamp(-4.0, 4.0) + 4.0) * (255.0 / 8.0)).to(torch.uint8)
+
+
+def q8_gelu_grad(codes):
+    x = (codes.double() * (8.0 / 255.0) - 4.0).requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    return x.grad.float()
+
+
+@pytest.mark.parametrize("M,N,K", [(640, 384, 384), (4096, 1536, 384), (200, 192, 128)])
+def test_gemm_gelu_epilogues_with_8bit_preactivation_codes(ops, M, N, K):
+    """DIG_EPI_GELU / DIG_EPI_GELU_BWD with aux_q8 (1-CTA kernel, TMA and generic epilogues): codes match the restated quantiser up
+    to one level at rounding ties, the backward equals dy.W x gelu'(decoded level), and it stays within 1.3e-2 of the exact gelu'."""
+    torch.manual_seed(5)
+    a, w = rnd(M, K, dtype=torch.bfloat16), rnd(N, K, scale=2.0 / K ** 0.5, dtype=torch.bfloat16)
+    bias = rnd(N)
+    acc = a.float() @ w.float().t() + bias
+    post, codes = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.zeros(M, N, device="cuda", dtype=torch.uint8)
+    ops.gemm(a, w, post, bias=bias, epilogue=ops.EPI_GELU, aux=codes)
+    assert torch.allclose(post.float(), torch.nn.functional.gelu(acc), atol=2e-2, rtol=8e-3)
+    diff = (codes.int() - q8_codes(acc).int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 2e-3      # fp32 accumulation order moves a value across a tie
+    assert acc.abs().max() > 4.0 and int(codes.min()) == 0 and int(codes.max()) == 255   # the clamp is exercised
+    wt = w.t().contiguous()
+    dh, cs = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.zeros(N, device="cuda")
+    ops.gemm(a, wt, dh, b_mn_major=True, epilogue=ops.EPI_GELU_BWD, aux=codes, colsum=cs)
+    plain = a.float() @ w.float().t()
+    ref = plain * q8_gelu_grad(codes)
+    assert torch.allclose(dh.float(), ref, atol=3e-2, rtol=1e-2)
+    assert torch.allclose(cs, dh.float().sum(0), atol=5e-2, rtol=1e-3)
+    x = acc.clone().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    assert float((q8_gelu_grad(codes) - x.grad).abs().max()) < 1.3e-2
+    assert float((q8_gelu_grad(codes) - x.grad).pow(2).mean().sqrt()) < 5e-3
+
+
 def test_gemm_unbuilt_combination_is_an_error(ops):
     a = rnd(128, 64, dtype=torch.bfloat16)
     with pytest.raises(ops.DigError):
