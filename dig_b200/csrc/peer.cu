@@ -7,6 +7,12 @@
 //   * MoCo key all-gather (concat_all_gather, M:580-591; C1): the L2-normalised keys of this rank are written by the normalising kernel's
 //     grid directly into every peer's key table, already in the [k1 of all ranks ; k2 of all ranks] order the logits GEMM consumes.
 //
+//   * Gradient averaging (DistributedDataParallel's bucket all-reduce, R:391; C2): the flat fp32 gradient buffer of every rank lives in an
+//     IPC-mapped allocation.  One kernel per step: rank r owns the r-th slice of the buffer, waits until every rank's backward has
+//     finished (flags), reads that slice from all W buffers over NVLink (128-bit loads), adds them in rank order, scales by 1/W and
+//     stores the result into all W buffers; a second flag round makes kernel completion mean "my whole buffer is averaged".  The sum is
+//     formed once per element, so every rank holds bit-identical gradients.
+//
 // Memory: every rank cudaMalloc's one workspace (dig_peer_alloc), the ranks exchange its IPC handle through torch.distributed and map
 // each other's (dig_peer_open).  Layout of a workspace (floats unless noted), W = world size, kPeerMaxFloats per message:
 //   [channel c][slot s in 0..1][source rank r] message area      (c < kPeerChannels)
@@ -64,6 +70,81 @@ peer_l2norm_allgather_kernel(PeerTable pt, const float* __restrict__ x, float* _
   }
   __syncthreads();
   if (is_last) peer_signal_and_wait(pt, world, rank, channel, slot, epoch);
+}
+
+// ---- gradient averaging over peer memory ------------------------------------------------------------------------------------------
+struct PeerGradTable {
+  float* grad[kPeerMaxRanks];
+};
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f4(float4* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Every thread block: wait until flag[channel][0][r] in OUR workspace has reached `value` for every source rank r.
+__device__ __forceinline__ void peer_wait_all(const PeerTable& pt, int world, int rank, int channel, uint32_t value) {
+  if ((int)threadIdx.x < world) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(pt.base[rank] + peer_flag_off(channel, 0, (int)threadIdx.x));
+    const long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
+      if (global_ns() - t0 > kPeerWaitNs) {
+        atomicExch(reinterpret_cast<unsigned int*>(pt.base[rank] + peer_err_off()), 1u);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+// n4 float4 elements per buffer; flag values of exchange e: 2e-1 = "my gradients are final", 2e = "my slice is stored everywhere".
+// Monotonic counters on one slot are safe: a rank can only signal 2e+1 after it has seen every 2e, and 2e+1 >= 2e for a late waiter.
+template <int W>
+__global__ void __launch_bounds__(512)
+peer_grad_allreduce_kernel(PeerTable pt, PeerGradTable gt, long long n4, int rank, int channel, uint32_t epoch) {
+  const uint32_t ready = 2u * epoch - 1u, done = 2u * epoch;
+  if (blockIdx.x == 0 && (int)threadIdx.x < W)     // stream order: every kernel that wrote this rank's gradients has completed
+    st_release_sys(reinterpret_cast<uint32_t*>(pt.base[threadIdx.x] + peer_flag_off(channel, 0, rank)), ready);
+  peer_wait_all(pt, W, rank, channel, ready);
+  const long long per = (n4 + W - 1) / W;
+  const long long lo = per * rank, hi = min(n4, lo + per);
+  const float inv = 1.0f / (float)W;
+  constexpr int U = 2;    // 2 x W 128-bit loads in flight per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
+    float4 v[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (i + u * stride < hi) v[u][r] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(gt.grad[r]) + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= hi) continue;
+      float4 s = v[u][0];
+#pragma unroll
+      for (int r = 1; r < W; ++r) { s.x += v[u][r].x; s.y += v[u][r].y; s.z += v[u][r].z; s.w += v[u][r].w; }
+      s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+#pragma unroll
+      for (int r = 0; r < W; ++r) st_relaxed_sys_f4(reinterpret_cast<float4*>(gt.grad[r]) + i + u * stride, s);
+    }
+  }
+  // last block of the grid: all slices of this rank are stored (fence + ticket) -> tell every peer, then wait for theirs
+  __shared__ int is_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(pt.base[rank] + peer_ticket_off(channel));
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < W) st_release_sys(reinterpret_cast<uint32_t*>(pt.base[threadIdx.x] + peer_flag_off(channel, 0, rank)), done);
+  peer_wait_all(pt, W, rank, channel, done);
 }
 
 }  // namespace dig
@@ -159,5 +240,30 @@ extern "C" int dig_peer_error(const int64_t* bases, int32_t world, int32_t rank,
   uint32_t v = 0;
   DIG_CHECK_CUDA(cudaMemcpy(&v, reinterpret_cast<const unsigned char*>((uintptr_t)bases[rank]) + peer_err_off(), sizeof(v), cudaMemcpyDeviceToHost));
   *err_out = (int32_t)v;
+  return 0;
+}
+
+extern "C" int dig_peer_grad_allreduce(const int64_t* bases, const int64_t* grad_bases, int32_t world, int32_t rank, int32_t channel,
+                                       int64_t epoch, int64_t n, int32_t blocks, void* stream) {
+  DIG_REQUIRE(bases && grad_bases && n > 0 && n % 4 == 0, "dig_peer_grad_allreduce: n must be a positive multiple of 4 (got %lld)", (long long)n);
+  DIG_REQUIRE(rank >= 0 && rank < world && channel >= 0 && channel < kPeerChannels && epoch >= 1 && epoch < (1ll << 30),
+              "dig_peer_grad_allreduce: bad rank/channel/epoch");
+  PeerTable pt;
+  if (int rc = fill_peer_table(&pt, bases, world)) return rc;
+  PeerGradTable gt;
+  for (int i = 0; i < kPeerMaxRanks; ++i) gt.grad[i] = i < world ? reinterpret_cast<float*>((uintptr_t)grad_bases[i]) : nullptr;
+  for (int i = 0; i < world; ++i) DIG_REQUIRE(gt.grad[i] != nullptr && ((uintptr_t)gt.grad[i] & 15) == 0, "dig_peer_grad_allreduce: rank %d has no (16-byte aligned) mapped gradient buffer", i);
+  if (blocks <= 0) blocks = num_sms();
+  const long long n4 = n / 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (world) {
+    case 2: peer_grad_allreduce_kernel<2><<<blocks, 512, 0, s>>>(pt, gt, n4, rank, channel, (uint32_t)epoch); break;
+    case 4: peer_grad_allreduce_kernel<4><<<blocks, 512, 0, s>>>(pt, gt, n4, rank, channel, (uint32_t)epoch); break;
+    case 8: peer_grad_allreduce_kernel<8><<<blocks, 512, 0, s>>>(pt, gt, n4, rank, channel, (uint32_t)epoch); break;
+    default:
+      set_last_error("dig_peer_grad_allreduce: built for 2, 4 or 8 ranks (got %d)", world);
+      return -1;
+  }
+  DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -7,7 +7,7 @@
 namespace dig {
 
 static constexpr int kPeerMaxRanks = 8;
-static constexpr int kPeerChannels = 4;
+static constexpr int kPeerChannels = 5;   // 0-2 SyncBatchNorm statistics, 3 keys, 4 gradient all-reduce
 static constexpr int kPeerMaxFloats = 8192;                       // 2 x 4096 columns (projector width, M:463-482)
 static constexpr long long kPeerWaitNs = 20ll * 1000 * 1000 * 1000;  // a peer that has not arrived after 20 s is gone: flag the error, do not hang
 

@@ -8,6 +8,7 @@ Channels (one exchange sequence per stream, identical on every rank):
   1  momentum forward BatchNorm statistics     (side stream)
   2  backward BatchNorm statistics             (main stream)
   3  key all-gather                            (side stream)
+  4  gradient all-reduce                       (main stream, last kernel of the backward)
 """
 import ctypes
 import os
@@ -17,7 +18,7 @@ import torch.distributed as dist
 
 from . import ops
 
-CH_ONLINE, CH_MOMENTUM, CH_BACKWARD, CH_KEYS = 0, 1, 2, 3
+CH_ONLINE, CH_MOMENTUM, CH_BACKWARD, CH_KEYS, CH_GRADS = 0, 1, 2, 3, 4
 MAX_FLOATS = 8192
 _MAX_RANKS = 8
 
@@ -62,7 +63,9 @@ class PeerComm:
         self.error = err
         self.bases = (ctypes.c_int64 * _MAX_RANKS)(*bases)
         self.keys_offset = koff.value
-        self.epoch = [0, 0, 0, 0]
+        self.epoch = [0, 0, 0, 0, 0]
+        self._group = group
+        self._shared = []          # [(own pointer, [mapped peer pointers])] of alloc_shared
         if not self.ok:
             self.close()
         dist.barrier(group=group)
@@ -75,6 +78,45 @@ class PeerComm:
         """Device address of this rank's key table for the exchange `epoch` ([2, W*Q, C] fp32, written by every rank's kernel)."""
         return self._own.value + self.keys_offset + (epoch & 1) * self.key_table_bytes
 
+    def alloc_shared(self, nbytes):
+        """COLLECTIVE: every rank allocates `nbytes` of device memory and maps every peer's allocation.  Returns (tensor-compatible own
+        address, ctypes int64[8] table of all ranks' addresses) or None when a rank failed (then nobody uses it)."""
+        lib = ops.load()
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        ok = 1
+        try:
+            ops._check(lib.dig_peer_alloc(int(nbytes), ctypes.byref(own), handle), "dig_peer_alloc")
+        except ops.DigError:
+            ok = 0
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, bytes(handle)), group=self._group)
+        mapped, bases = [], [0] * _MAX_RANKS
+        if all(g[0] for g in gathered):
+            try:
+                for r, g in enumerate(gathered):
+                    if r == self.rank:
+                        bases[r] = own.value
+                    else:
+                        p = ctypes.c_void_p()
+                        ops._check(lib.dig_peer_open(g[1], ctypes.byref(p)), "dig_peer_open")
+                        mapped.append(p)
+                        bases[r] = p.value
+            except ops.DigError:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._group)
+        if not int(flag.item()):
+            for p in mapped:
+                lib.dig_peer_close(p)
+            if own:
+                lib.dig_peer_free(own)
+            return None
+        self._shared.append((own, mapped))
+        return own.value, (ctypes.c_int64 * _MAX_RANKS)(*bases)
+
     def check(self):
         e = ctypes.c_int32()
         ops._check(ops.load().dig_peer_error(self.bases, self.world, self.rank, ctypes.byref(e)), "dig_peer_error")
@@ -86,9 +128,31 @@ class PeerComm:
         for p in self._mapped:
             lib.dig_peer_close(p)
         self._mapped = []
+        for own, mapped in getattr(self, "_shared", []):
+            for p in mapped:
+                lib.dig_peer_close(p)
+            lib.dig_peer_free(own)
+        self._shared = []
         if self._own:
             lib.dig_peer_free(self._own)
             self._own = ctypes.c_void_p()
+
+
+class _DeviceArray:
+    """Zero-copy torch view of raw device memory (torch.as_tensor understands __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def shared_float_buffer(comm, n):
+    """COLLECTIVE: a zero-initialised fp32 [n] tensor per rank in IPC-mapped memory + the table of every rank's address (or None)."""
+    r = comm.alloc_shared(4 * int(n))
+    if r is None:
+        return None
+    ptr, table = r
+    t = torch.as_tensor(_DeviceArray(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
+    return t, table
 
 
 _comm = {}

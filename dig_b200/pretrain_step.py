@@ -14,6 +14,7 @@ view, rows [B*256, 2B*256) the augmented view, exactly torch.cat([image, aug_ima
   * head activations          fp32 pre-BatchNorm, bf16 post-BatchNorm (GEMM operands)
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -120,6 +121,7 @@ class PretrainStep:
         self._mask_err = None      # (event, pinned int32[1]) of the previous forward's dig_mask_to_index error flag
         self._peer = None
         self._grad_flat = None
+        self._grad_peer = None      # table of every rank's flat gradient buffer when it lives in IPC-mapped memory
         # The momentum branch (EMA update + no-grad forward) and the online branch are independent until the InfoNCE logits: they run
         # on two streams so that one branch's HBM-bound kernels (LayerNorm, BatchNorm, casts) fill in under the other's GEMMs.
         import os
@@ -638,8 +640,20 @@ class PretrainStep:
         # tables of the multi-tensor grad-norm / AdamW launches are built once (rebuilding them costs synchronous pageable H2D copies).
         # If gradients of an earlier backward are still attached to the parameters (accumulation), they must not be overwritten.
         p0 = self._named[self.train_names[0]]
+        sync = getattr(model, "_dig_grad_sync", None)
+        world, _ = _world()
         if self._grad_flat is None:
-            self._grad_flat = torch.zeros(self.grad_total, dtype=F32, device=self.device)
+            # DigDataParallel on one NVSwitch node: the flat buffer lives in IPC-mapped memory, so that ONE kernel at the end of the backward
+            # averages it over the ranks through NVLink peer loads / stores (csrc/peer.cu) instead of 14 NCCL all-reduces that hold SMs
+            # next to the backward's statically scheduled persistent GEMMs (collective allocation: every rank's first backward).
+            self._grad_peer = None
+            if (sync is not None and world > 1 and self._peer is not None and os.environ.get("DIG_PEER_GRADS", "1") != "0"
+                    and world in (2, 4, 8) and self.grad_total % 4 == 0 and sync.process_group is None):
+                r = peer.shared_float_buffer(self._peer, self.grad_total)
+                if r is not None:
+                    self._grad_flat, self._grad_peer = r
+            if self._grad_flat is None:
+                self._grad_flat = torch.zeros(self.grad_total, dtype=F32, device=self.device)
             flat = self._grad_flat
         elif p0.grad is not None and p0.grad.data_ptr() == self._grad_flat.data_ptr():
             flat = torch.zeros(self.grad_total, dtype=F32, device=self.device)
@@ -647,10 +661,9 @@ class PretrainStep:
             flat = self._grad_flat
             flat.zero_()
         grads = self._grad_views(flat)
-        sync = getattr(model, "_dig_grad_sync", None)
-        world, _ = _world()
         self._sync_works = []
         self._sync_flat = flat if (sync is not None and world > 1) else None
+        self._sync_peer = self._grad_peer is not None and flat is self._grad_flat and self._peer is not None   # else: NCCL segments
         self._sync_group = sync.process_group if sync is not None else None
         Bf.zero_phase("bwd")
         g = Bf.get("bw.g", (M, d), F32)
@@ -710,13 +723,18 @@ class PretrainStep:
         for w in self._sync_works:                 # the current stream waits for the NCCL work (no host block)
             w.wait()
         self._sync_works = []
+        if self._sync_flat is not None and self._sync_peer:
+            # every gradient of this rank is final (main stream; the side stream's weight gradients were joined above)
+            pc = self._peer
+            call("dig_peer_grad_allreduce", pc.bases, self._grad_peer, pc.world, pc.rank, peer.CH_GRADS, pc.next_epoch(peer.CH_GRADS),
+                 self.grad_total, int(os.environ.get("DIG_PEER_GRAD_BLOCKS", "0")))
         self.saved = None
         return [grads[n] for n in self.train_names]
 
     def _allreduce_segment(self, key, stream=None, after=None):
         """DigDataParallel: average one finished segment of the flat gradient buffer over the ranks (async NCCL all-reduce, issued on
         `stream` -- the side stream during the encoder backward -- after the event `after` recorded on the chain stream)."""
-        if self._sync_flat is None:
+        if self._sync_flat is None or self._sync_peer:
             return
         a, b = self.grad_seg[key]
         cur = torch.cuda.current_stream()

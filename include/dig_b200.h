@@ -130,7 +130,7 @@ int dig_bn_bwd_apply(const float* dy, const float* x, const float* stats, const 
  * Replaces the torch.distributed calls of SyncBatchNorm (R:390: one tiny collective per BatchNorm layer, forward and
  * backward) and concat_all_gather (M:580-591).  Every rank owns a workspace (dig_peer_alloc) whose IPC handle the ranks
  * exchange out of band; `bases` is a HOST array of `world` int64 device addresses: this rank's own workspace at [rank],
- * the mapped peer workspaces elsewhere.  `channel` (0..3) names an independent exchange sequence -- one per stream -- and
+ * the mapped peer workspaces elsewhere.  `channel` (0..4) names an independent exchange sequence -- one per stream -- and
  * `epoch` counts the exchanges of that channel from 1; every rank must issue the same sequence per channel.  A wait that
  * times out (a peer died) sets an error word readable with dig_peer_error instead of hanging the GPU.                  */
 int dig_peer_workspace_bytes(int64_t key_table_bytes, int64_t* total_out, int64_t* keys_offset_out);
@@ -156,6 +156,14 @@ int dig_bn_bwd_stats_allreduce(const float* dy, const float* x, const float* sta
  * slot) at [half][rank*Q + i][C]; when the kernel completes, the table holds all ranks' keys.  local_copy may be NULL.  */
 int dig_peer_l2norm_allgather(const int64_t* bases, int32_t world, int32_t rank, int32_t channel, int64_t epoch, const float* x,
                               float* local_copy, int64_t Q, int32_t C, int64_t key_table_bytes, void* stream);
+/* Gradient averaging of the data-parallel step (torch DistributedDataParallel's bucket all-reduce, R:391) over peer memory:
+ * grad_bases[r] = device address of rank r's flat fp32 gradient buffer of n floats (this rank's own at [rank], the others
+ * IPC-mapped; allocate with dig_peer_alloc).  Rank r reads the r-th slice of all `world` buffers over NVLink, adds them in
+ * rank order, scales by 1/world and stores the result into all of them; when the kernel completes, this rank's whole buffer
+ * holds the average (bit-identical on every rank).  world in {2,4,8}; blocks <= 0: one per SM.  `channel` must be used by
+ * this exchange only (4).                                                                                                */
+int dig_peer_grad_allreduce(const int64_t* bases, const int64_t* grad_bases, int32_t world, int32_t rank, int32_t channel,
+                            int64_t epoch, int64_t n, int32_t blocks, void* stream);
 
 /* elementwise fp32 -> bf16 (n % 4 == 0). */
 int dig_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
