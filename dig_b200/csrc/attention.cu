@@ -786,12 +786,14 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   uint64_t* bar_sdp = bars + 10;
   uint64_t* bar_pds = bars + 11;
   uint64_t* bar_mma = bars + 12;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* bar_sc = bars + 13;     // compute -> MMA (256 arrivals): S, dP of the block are in registers, their TMEM columns may be overwritten
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * kHd;
   const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total = my_items * 4;   // blocks (it = 2 j + i) this CTA processes
+  long long* const dbg = (blockIdx.x == 0 && (warp == 8 || threadIdx.x == 0)) ? g_attn_dbg : nullptr;   // clock stamps (bring-up)
 
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -802,6 +804,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     mbar_init(bar_sdp, 1);
     mbar_init(bar_pds, 256);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_sc, 256);
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(tmem_holder, 512);
@@ -864,9 +867,19 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       for (int g = 0; g < total; ++g) {
         const int it = g & 3, j = it >> 1, i = it & 1, sl = qdo_slot(g);
         const uint32_t aQ = base + kBwdQdO + sl * 32768, adO = aQ + 16384, aK = base + kBwdKV + j * 32768;
+        // The next block's scores are issued as soon as this block's S, dP have left TMEM -- while the compute warps are still storing
+        // P / dS to shared memory -- so the tensor pipe's S,dP latency (8 MMAs + commit) hides behind those stores instead of
+        // following them; they also go ahead of this block's gradient products.
+        if (g + 1 < total) {
+          mbar_wait(bar_sc, (uint32_t)g & 1u);
+          tc_fence_after();
+          if (lane == 0) DIG_STAMP(0, g, 0);
+          issue_sdp(g + 1);
+          if (lane == 0) DIG_STAMP(0, g, 1);
+        }
         mbar_wait(bar_pds, (uint32_t)g & 1u);
         tc_fence_after();
-        if (g + 1 < total) issue_sdp(g + 1);   // the next block's scores go ahead of this block's gradient products
+        if (lane == 0) DIG_STAMP(0, g, 2);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (reduction over 128 queries)
@@ -887,6 +900,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           else if (it == 3) { tc_commit(&qdo_empty[sl]); tc_commit(&kv_empty[1]); }
         }
         __syncwarp();
+        if (lane == 0) DIG_STAMP(0, g, 3);
       }
     }
   } else {
@@ -942,31 +956,49 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
           Dr[ii] = Dsum[(long long)(row0 + ii * 128 + t) * heads + head];
         }
       }
+      DIG_STAMP(1, g, 0);
       mbar_wait(bar_sdp, (uint32_t)g & 1u);
       tc_fence_after();
+      DIG_STAMP(1, g, 1);
       // phase A: S, dP (TMEM) -> P, dS as packed bf16 in registers; overlaps the tensor pipe's dV,dK,dQ of the previous block
+      // (the second 32-column chunk's TMEM loads are in flight while the first chunk is processed)
       uint32_t pp[32], ds[32];
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t sv[32], gv[32];
-        tmem_ld32(tl + cS + hh * 64 + c, sv);
-        tmem_ld32(tl + cdP + hh * 64 + c, gv);
+      {
+        uint32_t sv0[32], gv0[32], sv1[32], gv1[32];
+        tmem_ld32(tl + cS + hh * 64, sv0);
+        tmem_ld32(tl + cdP + hh * 64, gv0);
         tmem_ld_wait();
+        tmem_ld32(tl + cS + hh * 64 + 32, sv1);
+        tmem_ld32(tl + cdP + hh * 64 + 32, gv1);
 #pragma unroll
         for (int q = 0; q < 32; q += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[q]), sl2, -Lr[i]));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[q + 1]), sl2, -Lr[i]));
-          const float d0 = p0 * (__uint_as_float(gv[q]) - Dr[i]);
-          const float d1 = p1 * (__uint_as_float(gv[q + 1]) - Dr[i]);
-          pp[(c + q) >> 1] = pack_bf16(p0, p1);
-          ds[(c + q) >> 1] = pack_bf16(d0, d1);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv0[q]), sl2, -Lr[i]));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv0[q + 1]), sl2, -Lr[i]));
+          const float d0 = p0 * (__uint_as_float(gv0[q]) - Dr[i]);
+          const float d1 = p1 * (__uint_as_float(gv0[q + 1]) - Dr[i]);
+          pp[q >> 1] = pack_bf16(p0, p1);
+          ds[q >> 1] = pack_bf16(d0, d1);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_sc);     // S, dP of this block are in registers: the MMA warp may issue the next block's scores
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv1[q]), sl2, -Lr[i]));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv1[q + 1]), sl2, -Lr[i]));
+          const float d0 = p0 * (__uint_as_float(gv1[q]) - Dr[i]);
+          const float d1 = p1 * (__uint_as_float(gv1[q + 1]) - Dr[i]);
+          pp[(32 + q) >> 1] = pack_bf16(p0, p1);
+          ds[(32 + q) >> 1] = pack_bf16(d0, d1);
         }
       }
+      DIG_STAMP(1, g, 2);
       // phase B: the previous block's gradient products have read the P / dS buffers
       if (g > 0) {
         mbar_wait(bar_mma, (uint32_t)(g - 1) & 1u);
         tc_fence_after();
       }
+      DIG_STAMP(1, g, 3);
       if (it == 2) {
         // dV_0, dK_0 are final (block 1): TMEM -> the idle P / dS buffers -> two TMA stores
         stage_tile(cdV, sP_s, 1.0f);
@@ -987,6 +1019,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         if (storer) tma_store_wait_read_all();
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      DIG_STAMP(1, g, 4);
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const uint32_t off = (uint32_t)hh * 16384u + sw128_offset((uint32_t)t, (uint32_t)jj);
@@ -996,6 +1029,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_pds);
+      DIG_STAMP(1, g, 5);
     }
     if (total > 0) {
       mbar_wait(bar_mma, (uint32_t)(total - 1) & 1u);

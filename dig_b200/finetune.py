@@ -365,13 +365,18 @@ class FinetuneStep(PretrainStep):
             # ---- encoder-decoder attention (transformer_layer.py:106-112) ----
             call("dig_cast_f32_bf16", gx, gxb, Md * dm)
             dca = Bf.get("b.dca", (Md, dm), BF16)
-            ops.gemm(gxb, S_[p + "enc_attn.fc.weight"], dca, b_mn_major=True)
+            # the dgrad of the output projection also emits D = rowsum(dO o O) per head (DIG_EPI_ROWDOT), which lets the cross-attention
+            # backward run on the persistent kernel (as in the encoder) instead of the one-shot one that recomputes D from O
+            dsum_s = Bf.get("b.dsum_s", (Md, H), F32)
+            ops.gemm(gxb, S_[p + "enc_attn.fc.weight"], dca, b_mn_major=True, epilogue=ops.EPI_ROWDOT, aux=a["ca"], rowdot=dsum_s)
             wgrad(gxb, a["ca"], grads[p + "enc_attn.fc.weight"])
             dqc = Bf.get("b.dqc", (Md, dm), BF16)
             dattx = self._zero_once("b.dattx", (M, dm), BF16)          # rows >= T of every 256-row tile stay zero
             dattx.view(B, TOK, dm)[:, :T].copy_(dca.view(B, T, dm))
             dqkvx = Bf.get("b.dqkvx", (M, 3 * dm), BF16)
-            ops.attention_bwd(a["qkvx"], a["attx"], dattx, a["lse_c"], dqkvx, H, self.scale)
+            dsumx = self._zero_once("b.dsumx", (M, H), F32)            # D of the padding rows is zero (their dO is)
+            dsumx.view(B, TOK, H)[:, :T].copy_(dsum_s.view(B, T, H))
+            ops.attention_bwd_d(a["qkvx"], dattx, a["lse_c"], dsumx, dqkvx, H, self.scale)
             dqc.view(B, T, dm).copy_(dqkvx.view(B, TOK, 3 * dm)[:, :T, :dm])
             dkv = dqkvx[:, dm:]
             wgrad(dqc, a["h2"], grads[p + "enc_attn.linear_q.weight"])

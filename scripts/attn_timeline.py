@@ -29,17 +29,19 @@ for r in range(3):
     for n in range(11):
         print("   item %2d: " % n + " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[r, n]))
 
-# ---- backward (one-shot kernel): CTA 0 ----
+# ---- backward (persistent kernel): CTA 0, first 12 blocks (3 items x 4 blocks of 128 queries x 128 keys) ----
 dout = torch.randn(S * 256, d, device="cuda").bfloat16(); dqkv = torch.empty_like(qkv)
-for _ in range(2): ops.attention_bwd(qkv, out, dout, lse, dqkv, h, scale)
+dsum = (dout.float() * out.float()).view(S * 256, h, 64).sum(-1).contiguous()
+for _ in range(2): ops.attention_bwd_d(qkv, dout, lse, dsum, dqkv, h, scale)
 buf.zero_()
 lib.dig_attention_debug_buffer(ctypes.c_void_p(buf.data_ptr()))
-ops.attention_bwd(qkv, out, dout, lse, dqkv, h, scale)
+e0.record(); ops.attention_bwd_d(qkv, dout, lse, dsum, dqkv, h, scale); e1.record()
 torch.cuda.synchronize()
+print('backward kernel (events): %.1f us' % (e0.elapsed_time(e1) * 1e3))
 lib.dig_attention_debug_buffer(None)
 b = buf.cpu()
 t0 = int(b[b > 0].min())
-print("bwd MMA thread : row0 = start | loads issued | loads landed ; rows 1-4 (it): S,dP committed | pds seen | dV,dK,dQ committed ; row5: - | end | after sync")
-for n in range(6): print("   ", " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[0, n]))
-print("bwd thread 0   : row0 = start | D,lse done ; rows 1-4 (it): top | sdp seen | bufs free | pds arrive | mma seen | dV,dK stored ; row5: loop done | end | after sync")
-for n in range(6): print("   ", " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[1, n]))
+print("bwd MMA warp (per block g): S,dP of g consumed (bar_sc) seen | S,dP(g+1) issued | P,dS of g stored (bar_pds) seen | dV,dK,dQ(g) issued")
+for n in range(12): print("   block %2d: " % n + " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[0, n][:4]))
+print("bwd compute thread 0 (per block g): loop top | S,dP seen | phase A done | previous dV,dK,dQ done (bar_mma) | staging done | P,dS stored, arrive")
+for n in range(12): print("   block %2d: " % n + " ".join("%7d" % (int(x) - t0) if x > 0 else "      -" for x in b[1, n][:6]))
