@@ -768,13 +768,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 // Warps 0-7 compute (warp & 3 = TMEM lane quarter, warp >> 2 = which 64 key columns / 32 output columns), warp 8 = MMA issue + TMEM
 // owner, warp 9 = TMA producer.
 // ------------------------------------------------------------------------------------------------
+#ifndef DIG_ATTN_BWD_STG
+#define DIG_ATTN_BWD_STG 0   // experiment, measured SLOWER (146.7 vs 107.5 us): see stg_regs below
+#endif
 static constexpr int kBwdPThreads = 320;
 static constexpr uint32_t kBwdQdO = 0, kBwdKV = 98304, kBwdP = 163840, kBwdDS = 196608, kBwdBars = 229376;
 
 __global__ void __launch_bounds__(kBwdPThreads, 1)
 attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ lse, const float* __restrict__ Dsum, int heads,
-                        float scale, int num_items) {
+                        float scale, int num_items, __nv_bfloat16* __restrict__ dqkv_out) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -911,10 +914,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const float sl2 = scale * kLog2e;
     const uint32_t sP_s = smem_u32(smem) + kBwdP, sdS_s = smem_u32(smem) + kBwdDS;
     const bool storer = (warp == 0 && lane == 0);
-    auto stage_tile = [&](uint32_t tcol, uint32_t dst_s, float mul) {
-      uint32_t v[32];
-      tmem_ld32(tl + tcol + hh * 32, v);
-      tmem_ld_wait();
+    auto stage_regs = [&](const uint32_t (&v)[32], uint32_t dst_s, float mul) {
 #pragma unroll
       for (int q = 0; q < 32; q += 8) {
         uint4 p;
@@ -925,12 +925,49 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         sts_u4(dst_s + sw128_offset((uint32_t)t, (uint32_t)((hh * 32 + q) >> 3)), p);
       }
     };
-    // dV_1, dK_1, dQ_0, dQ_1 of the item (head, row0): the four 16 KB halves of the P / dS buffers stage one tile each
+    // DIG_ATTN_BWD_STG=1 (experiment): finished gradient tiles go from registers straight to global memory (each thread owns 64
+    // contiguous bytes of a row: 4 x STG.128).  The TMA staging in the P / dS buffers costs 2-3.4 k clocks per window (clock stamps: two
+    // block-wide barriers plus the wait until the TMA engine has read 32-64 KB back out of shared memory), but the row-per-thread stores
+    // are worse: every STG.128 touches 32 different lines and the window grew to 5.2 k clocks (kernel 107.5 -> 146.7 us).
+    auto stg_regs = [&](const uint32_t (&v)[32], int col, int row, float mul) {
+      uint4* dst = reinterpret_cast<uint4*>(dqkv_out + (long long)(row + t) * (3 * d) + col + hh * 32);
+#pragma unroll
+      for (int q = 0; q < 32; q += 8) {
+        uint4 p;
+        p.x = pack_bf16(__uint_as_float(v[q + 0]) * mul, __uint_as_float(v[q + 1]) * mul);
+        p.y = pack_bf16(__uint_as_float(v[q + 2]) * mul, __uint_as_float(v[q + 3]) * mul);
+        p.z = pack_bf16(__uint_as_float(v[q + 4]) * mul, __uint_as_float(v[q + 5]) * mul);
+        p.w = pack_bf16(__uint_as_float(v[q + 6]) * mul, __uint_as_float(v[q + 7]) * mul);
+        dst[q >> 3] = p;
+      }
+    };
     auto store_item_tail = [&](int head, int row0) {
-      stage_tile(cdV, sP_s, 1.0f);
-      stage_tile(cdK, sdS_s, scale);
-      stage_tile(cdQ, sP_s + 16384, scale);
-      stage_tile(cdQ + 64, sdS_s + 16384, scale);
+#if DIG_ATTN_BWD_STG
+      uint32_t v0[32], v1[32], v2[32], v3[32];
+      tmem_ld32(tl + cdV + hh * 32, v0);
+      tmem_ld32(tl + cdK + hh * 32, v1);
+      tmem_ld32(tl + cdQ + hh * 32, v2);
+      tmem_ld32(tl + cdQ + 64 + hh * 32, v3);
+      tmem_ld_wait();
+      tc_fence_before();
+      stg_regs(v0, 2 * d + head * kHd, row0 + 128, 1.0f);
+      stg_regs(v1, d + head * kHd, row0 + 128, scale);
+      stg_regs(v2, head * kHd, row0, scale);
+      stg_regs(v3, head * kHd, row0 + 128, scale);
+      return;
+#endif
+      {   // all four TMEM loads in flight before the first conversion
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld32(tl + cdV + hh * 32, v0);
+        tmem_ld32(tl + cdK + hh * 32, v1);
+        tmem_ld32(tl + cdQ + hh * 32, v2);
+        tmem_ld32(tl + cdQ + 64 + hh * 32, v3);
+        tmem_ld_wait();
+        stage_regs(v0, sP_s, 1.0f);
+        stage_regs(v1, sdS_s, scale);
+        stage_regs(v2, sP_s + 16384, scale);
+        stage_regs(v3, sdS_s + 16384, scale);
+      }
       tc_fence_before();
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -942,7 +979,19 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tma_store_commit();
       }
     };
-    float Dr[2] = {0.f, 0.f}, Lr[2] = {0.f, 0.f};
+    // Row statistics (log-sum-exp, D) of an item are fetched one item ahead (during its predecessor's third block): read at the item's
+    // start, the two dependent global loads stalled every compute warp for ~2 k clocks per item (clock stamps).
+    float Dr[2] = {0.f, 0.f}, Lr[2] = {0.f, 0.f}, Dn[2] = {0.f, 0.f}, Ln[2] = {0.f, 0.f};
+    auto fetch_stats = [&](int item) {
+      const int w = (int)blockIdx.x + item * (int)gridDim.x;
+      const int hd = w % heads, sq = w / heads;
+#pragma unroll
+      for (int ii = 0; ii < 2; ++ii) {
+        Ln[ii] = lse[((long long)sq * heads + hd) * kTok + ii * 128 + t];
+        Dn[ii] = Dsum[((long long)sq * kTok + ii * 128 + t) * heads + hd];
+      }
+    };
+    if (total > 0) fetch_stats(0);
     int head = 0, row0 = 0, prev_head = 0, prev_row0 = 0;
     for (int g = 0; g < total; ++g) {
       const int it = g & 3, i = it & 1;
@@ -951,10 +1000,9 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         const int w = (int)blockIdx.x + (g >> 2) * (int)gridDim.x;
         head = w % heads; row0 = (w / heads) * kTok;
 #pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-          Lr[ii] = lse[((long long)(row0 / kTok) * heads + head) * kTok + ii * 128 + t] * kLog2e;
-          Dr[ii] = Dsum[(long long)(row0 + ii * 128 + t) * heads + head];
-        }
+        for (int ii = 0; ii < 2; ++ii) { Lr[ii] = Ln[ii] * kLog2e; Dr[ii] = Dn[ii]; }
+      } else if (it == 2 && g + 2 < total) {
+        fetch_stats((g >> 2) + 1);
       }
       DIG_STAMP(1, g, 0);
       mbar_wait(bar_sdp, (uint32_t)g & 1u);
@@ -999,10 +1047,25 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         tc_fence_after();
       }
       DIG_STAMP(1, g, 3);
-      if (it == 2) {
+      if (it == 2 && DIG_ATTN_BWD_STG) {
+        // dV_0, dK_0 are final (block 1)
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tl + cdV + hh * 32, v0);
+        tmem_ld32(tl + cdK + hh * 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        stg_regs(v0, 2 * d + head * kHd, row0, 1.0f);
+        stg_regs(v1, d + head * kHd, row0, scale);
+      } else if (it == 2) {
         // dV_0, dK_0 are final (block 1): TMEM -> the idle P / dS buffers -> two TMA stores
-        stage_tile(cdV, sP_s, 1.0f);
-        stage_tile(cdK, sdS_s, scale);
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tl + cdV + hh * 32, v0);
+          tmem_ld32(tl + cdK + hh * 32, v1);
+          tmem_ld_wait();
+          stage_regs(v0, sP_s, 1.0f);
+          stage_regs(v1, sdS_s, scale);
+        }
         tc_fence_before();
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1016,8 +1079,10 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       } else if (it == 0 && g > 0) {
         // the previous item is complete (its block 3): drain its last four tiles, then reuse the buffers for this item's block 0
         store_item_tail(prev_head, prev_row0);
-        if (storer) tma_store_wait_read_all();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!DIG_ATTN_BWD_STG) {
+          if (storer) tma_store_wait_read_all();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
       }
       DIG_STAMP(1, g, 4);
 #pragma unroll
@@ -1138,7 +1203,8 @@ extern "C" int dig_attention_bwd_d(const void* qkv, const void* dout, const floa
   if (!set) { DIG_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
   const int items = (int)(num_seqs * heads);
   const int ctas = items < num_sms() ? items : num_sms();
-  DIG_CHECK_CUDA(launch_pdl(attn_bwd_persist_kernel, dim3(ctas), dim3(kBwdPThreads), smem, s, tq, td, tg, lse, dsum, heads, scale, items));
+  DIG_CHECK_CUDA(launch_pdl(attn_bwd_persist_kernel, dim3(ctas), dim3(kBwdPThreads), smem, s, tq, td, tg, lse, dsum, heads, scale, items,
+                            reinterpret_cast<__nv_bfloat16*>(dqkv)));
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
