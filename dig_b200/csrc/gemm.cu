@@ -224,7 +224,7 @@ static int launch_gemm(const dig_gemm_t* g, cudaStream_t stream) {
     if (rc) return rc;
     if (epi_is_q8(MODE)) rc = make_tmap_u8_2d(&tx, g->aux, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32);
     else if ((epi_is_gelu(MODE) && g->aux != nullptr) || epi_is_gelu_bwd(MODE) || MODE == DIG_EPI_ROWDOT) rc = make_tmap_2d(&tx, g->aux, 0, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldaux, 32, 64);
-    else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)g->M, (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
+    else if (MODE == DIG_EPI_LINEAR && OUT_F32 && g->residual) rc = make_tmap_2d(&tx, g->residual, 1, (uint64_t)(g->res_row_mod > 0 ? g->res_row_mod : g->M), (uint64_t)g->N, (uint64_t)g->ldr, 32, 32);
     if (rc) return rc;
   }
 

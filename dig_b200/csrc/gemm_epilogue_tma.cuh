@@ -58,17 +58,21 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
   const uint32_t q8_row = (uint32_t)lane * 64u, q8_sw = ((uint32_t)lane >> 1) & 3u;
   const uint32_t lut_s = smem_u32(cta_colsum) + 2048u * 4u;
   const uint32_t ld_bytes = (epi_is_gelu_bwd(MODE) && q8) ? kStageTileBytes / 2 : kStageTileBytes;
+  // patch embed (V:95-99): the residual is the position table, indexed by row % res_row_mod (a multiple of 32, so a 32-row tile never
+  // straddles the wrap), and rows flagged in row_mask are replaced by the mask token before the table is added
+  const int aux_row = (MODE == DIG_EPI_LINEAR && ep.res_row_mod > 0) ? (int)(row_base % (int)ep.res_row_mod) : row_base;
+  const bool row_masked = MODE == DIG_EPI_LINEAR && ep.row_mask != nullptr && row_base + lane < ep.M && ep.row_mask[row_base + lane] != 0;
 
   // first group's operand load, before the accumulator wait
   if (lane == 0) tma_store_wait_read_all();       // staging tiles of the previous output tile are free again
   __syncwarp();
   if (has_ld && half < NGT && lane == 0) {
     mbar_expect_tx(&st.ld_bar[0], ld_bytes);
-    tma_load_2d_addr(st.stage_s, tm_aux, &st.ld_bar[0], n0 + half * G, row_base);
+    tma_load_2d_addr(st.stage_s, tm_aux, &st.ld_bar[0], n0 + half * G, aux_row);
 #if DIG_EPI_EARLY_LD
     if (half + 2 < NGT) {   // the second group's operand as well: both staging tiles are free here, and the load then has the accumulator
       mbar_expect_tx(&st.ld_bar[1], ld_bytes);   // wait plus one whole group of math to arrive (it waited ~15 % of the epilogue's time)
-      tma_load_2d_addr(st.stage_s + kStageTileBytes, tm_aux, &st.ld_bar[1], n0 + (half + 2) * G, row_base);
+      tma_load_2d_addr(st.stage_s + kStageTileBytes, tm_aux, &st.ld_bar[1], n0 + (half + 2) * G, aux_row);
     }
 #endif
   }
@@ -101,7 +105,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
       if (!last && k >= kFirstPrefetch && lane == 0) {  // prefetch the next group's operand into the other staging tile
         uint64_t* nb = &st.ld_bar[(k + 1) & 1];
         mbar_expect_tx(nb, ld_bytes);
-        tma_load_2d_addr(st.stage_s + (uint32_t)((k + 1) & 1) * kStageTileBytes, tm_aux, nb, gcol + 2 * G, row_base);
+        tma_load_2d_addr(st.stage_s + (uint32_t)((k + 1) & 1) * kStageTileBytes, tm_aux, nb, gcol + 2 * G, aux_row);
       }
       if (k & 1) { mbar_wait(&st.ld_bar[1], st.uses1 & 1); ++st.uses1; }
       else { mbar_wait(&st.ld_bar[0], st.uses0 & 1); ++st.uses0; }
@@ -146,6 +150,7 @@ __device__ __forceinline__ void epilogue_warp_tile_tma(const GemmEpilogue& ep, c
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + min(gcol + 4 * j, N - 4)));
             f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
           }
+          if (row_masked) f = __ldg(reinterpret_cast<const float4*>(ep.row_mask_value + min(gcol + 4 * j, N - 4)));
           if (has_ld) {
             const float4 r4 = lds_f4(a);
             f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
@@ -267,7 +272,8 @@ static inline bool tma_epilogue_ok(const dig_gemm_t* g) {
   if (enabled < 0) { const char* e = getenv("DIG_GEMM_TMA_EPI"); enabled = (e && e[0] == '0') ? 0 : 1; }
   if (!enabled) return false;
   const int es = g->out_fp32 ? 4 : 2;
-  if (g->row_mask || g->res_row_mod > 0) return false;
+  if ((g->row_mask || g->res_row_mod > 0) && !(g->out_fp32 && g->epilogue == DIG_EPI_LINEAR && g->res_row_mod % 32 == 0 && g->split_k <= 1)) return false;
+  if (g->res_row_mod > 0 && !g->residual) return false;
   if (g->epilogue == DIG_EPI_RELU_MASK) return false;
   if ((g->N * es) % 16 || (g->ldo * es) % 16 || ((uintptr_t)g->out & 15)) return false;
   if (g->epilogue == DIG_EPI_GELU || g->epilogue == DIG_EPI_GELU_BWD || g->epilogue == DIG_EPI_ROWDOT) {

@@ -9,6 +9,7 @@
     a non-finite loss still never reaches the weights: the optimizer launch is guarded by the loss value on the device.
 """
 import math
+import os
 import sys
 
 import numpy as np
@@ -50,6 +51,50 @@ def masked_pixel_mse(pred, images, mask_view0):
     loss = _MaskedPixelMSE.apply(pred, images.contiguous(), idx)
     loss._dig_mask_err = err      # device flag: some sample did not have exactly n masked patches (train_one_epoch reads it back)
     return loss
+
+
+class _DevicePrefetch:
+    """Iterates a loader one batch ahead: the (pinned) host tensors of batch n+1 are copied to the device on a side stream while step n
+    computes, so the ~13 MB of crops per step cross PCIe under the previous step instead of in front of this one (the reference issues
+    `.to(device, non_blocking=True)` on the compute stream, E:96-100).  Same batches, same order; anything that is not a tuple of CPU
+    tensors passes through untouched."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+        self.stream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, item):
+        batch = item[0]
+        if (self.stream is None or not isinstance(batch, (tuple, list)) or len(batch) != 3
+                or not all(isinstance(t, torch.Tensor) and not t.is_cuda for t in batch)):
+            return item, None
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.stream):
+            moved = tuple(t.to(self.device, non_blocking=True) for t in batch)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        for t in moved:
+            t.record_stream(main)          # allocated on the copy stream, consumed on the compute stream
+        return (moved,) + tuple(item[1:]), ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            staged = self._stage(next(it))
+        except StopIteration:
+            return
+        while staged is not None:
+            cur, ev = staged
+            try:
+                staged = self._stage(next(it))
+            except StopIteration:
+                staged = None
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+            yield cur
 
 
 def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader, word_data_loader, optimizer, device, epoch,
@@ -111,7 +156,8 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
             log_writer.update(grad_norm=packed[7], head="opt")
             log_writer.set_step()
 
-    for step, (batch, text, text_lens) in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
+    feed = data_loader if os.environ.get("DIG_PREFETCH", "1") == "0" else _DevicePrefetch(data_loader, device)
+    for step, (batch, text, text_lens) in enumerate(metric_logger.log_every(feed, print_freq, header)):
         it = start_steps + step
         if lr_schedule_values is not None or wd_schedule_values is not None:                      # E:60-66
             for group in optimizer.param_groups:

@@ -61,6 +61,19 @@ def test_residual_fp32_epilogue_at_65536_rows(ops, N, K):
     _close(out, ref, 1e-3, 1e-4, "proj/fc2+residual")
 
 
+def test_patch_embed_epilogue_at_65536_rows(ops):
+    """gemm2<192,...,LINEAR,fp32,TMA> as the 4x4 patch embedding (F:190-196, V:95-99): K = 48 im2col columns, bias, mask-token rows and
+    the position table indexed modulo 256 -- the TMA epilogue's row-mask / row-modulo path."""
+    torch.manual_seed(15)
+    a, w, bias = rnd(MTOK, 48, dtype=torch.bfloat16), rnd(384, 48, scale=0.1, dtype=torch.bfloat16), rnd(384)
+    mask = (torch.rand(MTOK, device="cuda") < 0.7).to(torch.uint8)
+    tok, pos = rnd(384), rnd(256, 384)
+    out = torch.empty(MTOK, 384, device="cuda")
+    ops.gemm(a, w, out, bias=bias, residual=pos, res_row_mod=256, row_mask=mask, row_mask_value=tok)
+    ref = torch.where(mask.bool()[:, None], tok.expand(MTOK, 384), a.float() @ w.float().t() + bias) + pos.repeat(MTOK // 256, 1)
+    _close(out, ref, 1e-3, 1e-4, "patch embed")
+
+
 def test_qkv_bf16_epilogue_at_65536_rows(ops):
     """gemm2<192,...,LINEAR,bf16,TMA>: qkv projection with the fused [q_bias|0|v_bias] (F:91-93)."""
     torch.manual_seed(12)
