@@ -245,6 +245,8 @@ class Workload:
             if wrapper == "torch":
                 # the reference runner's wrapper (R:391)
                 net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], find_unused_parameters=True)
+            elif wrapper == "none":
+                pass    # experiment only: no gradient averaging (with DIG_BENCH_NO_SYNCBN=1 the ranks are nearly independent replicas)
             else:
                 from dig_b200.parallel import DigDataParallel
                 net = DigDataParallel(net)     # flat-buffer gradient averaging overlapped with the backward (dig_b200/parallel.py)
@@ -339,6 +341,11 @@ def timed_steps(wl, steps, warmup, world):
     launches = ops.launch_count() - n0
     t = torch.tensor([e0.elapsed_time(e1) / steps], device=wl.dev)
     if world > 1:
+        if os.environ.get("DIG_BENCH_RANK_TIMES") == "1":      # experiment: every rank's own figure (rank skew)
+            all_t = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(all_t, t)
+            if dist.get_rank() == 0:
+                print("per-rank ms/step:", ["%.3f" % float(x.item()) for x in all_t], file=sys.stderr)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item()), float(last), launches
 

@@ -1,9 +1,11 @@
+#!/bin/bash
+# final profile pass of a round (under gpurun): per-launch metrics of one step, ncu --set full of the top kernels, fine-tune kernel list
 set -x
-cd $GRAFT_REPO_ROOT
+cd /root/repo
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
-timeout 600 python -m pytest tests/test_gpu_finetune.py tests/test_gpu_kernels.py -m gpu -q -p no:cacheprovider 2>&1 | grep -E "passed|failed|^E |^FAILED" | head
-python scripts/profile_finetune.py 256 2>&1 | grep -v "branch\|Warn\|warn" > gpurun_out/r2k_finetune_profile.txt; head -8 gpurun_out/r2k_finetune_profile.txt
-DIG_TWO_STREAMS=0 bash scripts/ncu_step_metrics.sh r2 128 2>&1 | tail -3
-bash scripts/ncu_capture.sh r2 128 2>&1 | tail -12
-ls -la gpurun_out | grep r2_ | head -40
+TAG=${1:-r2}
+python scripts/profile_finetune.py 256 2>&1 | grep -v "branch\|Warn\|warn" > gpurun_out/${TAG}_finetune_profile.txt; head -5 gpurun_out/${TAG}_finetune_profile.txt
+DIG_TWO_STREAMS=0 bash scripts/ncu_step_metrics.sh ${TAG} 128 2>&1 | tail -3
+bash scripts/ncu_capture.sh ${TAG} 128 2>&1 | tail -12
+python scripts/gaps.py 128 > gpurun_out/${TAG}_gaps.txt 2>&1; head -12 gpurun_out/${TAG}_gaps.txt
+ls -la gpurun_out | grep ${TAG}_ | head -40

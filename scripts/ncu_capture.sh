@@ -12,8 +12,8 @@ cap() {  # name regex skip
   ncu -i gpurun_out/${TAG}_$1.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/${TAG}_$1.source.csv.gz
   rm -f gpurun_out/${TAG}_$1.ncu-rep
 }
-cap fc1_gelu   'gemm2_bf16_tcgen05<[^,]*256, [^,]*0, [^,]*0, [^,]*1, [^,]*0, [^,]*1>' 14
-cap gelu_bwd   'gemm2_bf16_tcgen05<[^,]*256, [^,]*0, [^,]*1, [^,]*2, [^,]*0, [^,]*1>' 5
+cap fc1_gelu   'gemm2_bf16_tcgen05<[^,]*256, [^,]*0, [^,]*0, [^,]*6, [^,]*0, [^,]*1>' 8    # fc1 + GELU, 8-bit pre-activation codes (online branch)
+cap gelu_bwd   'gemm2_bf16_tcgen05<[^,]*256, [^,]*0, [^,]*1, [^,]*7, [^,]*0, [^,]*1>' 5    # fc2 dgrad x gelu'(8-bit level)
 cap wgrad      'gemm2_bf16_tcgen05<[^,]*256, [^,]*1, [^,]*1, [^,]*4, [^,]*1, [^,]*1>' 20 3
 cap res_f32    'gemm2_bf16_tcgen05<[^,]*192, [^,]*0, [^,]*0, [^,]*0, [^,]*1, [^,]*1>' 30 2
 cap qkv        'gemm2_bf16_tcgen05<[^,]*192, [^,]*0, [^,]*0, [^,]*0, [^,]*0, [^,]*1>' 14
@@ -21,4 +21,4 @@ cap dgrad      'gemm2_bf16_tcgen05<[^,]*128, [^,]*0, [^,]*1, [^,]*0, [^,]*0, [^,
 cap attn_fwd   'attn_fwd_persist_kernel' 14
 cap attn_bwd   'attn_bwd_persist_kernel' 5
 cap ln_bwd     'layernorm_bwd_kernel' 5
-cap ln_fwd     'layernorm_fwd_kernel' 30
+cap ln_fwd     'layernorm_fwd_vec_kernel' 30
