@@ -94,15 +94,20 @@ __device__ __forceinline__ void peer_wait_all(const PeerTable& pt, int world, in
         atomicExch(reinterpret_cast<unsigned int*>(pt.base[rank] + peer_err_off()), 1u);
         break;
       }
+      __nanosleep(100);    // the small-block variant shares its SM with a GEMM / attention CTA: do not burn their issue slots
     }
   }
   __syncthreads();
 }
 // n4 float4 elements per buffer; flag values of exchange e: 2e-1 = "my gradients are final", 2e = "my slice is stored everywhere".
 // Monotonic counters on one slot are safe: a rank can only signal 2e+1 after it has seen every 2e, and 2e+1 >= 2e for a late waiter.
-template <int W>
-__global__ void __launch_bounds__(512)
-peer_grad_allreduce_kernel(PeerTable pt, PeerGradTable gt, long long n4, int rank, int channel, uint32_t epoch) {
+// THREADS = 512, U = 2: one block per SM, for the exchange at the end of the backward (nothing else runs).  THREADS = 128, <= 64
+// registers: blocks small enough to be co-resident with the persistent GEMM / attention CTAs (which leave ~11 K registers and 1 700
+// thread slots per SM), for the exchanges issued from the side stream in the middle of the backward -- a kernel that needs whole SMs
+// makes every statically scheduled persistent GEMM launched beside it wait for its last CTAs.
+template <int W, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 8 : 1)
+peer_grad_allreduce_kernel(PeerTable pt, PeerGradTable gt, long long off4, long long n4, int rank, int channel, uint32_t epoch) {
   const uint32_t ready = 2u * epoch - 1u, done = 2u * epoch;
   if (blockIdx.x == 0 && (int)threadIdx.x < W)     // stream order: every kernel that wrote this rank's gradients has completed
     st_release_sys(reinterpret_cast<uint32_t*>(pt.base[threadIdx.x] + peer_flag_off(channel, 0, rank)), ready);
@@ -110,7 +115,6 @@ peer_grad_allreduce_kernel(PeerTable pt, PeerGradTable gt, long long n4, int ran
   const long long per = (n4 + W - 1) / W;
   const long long lo = per * rank, hi = min(n4, lo + per);
   const float inv = 1.0f / (float)W;
-  constexpr int U = 2;    // 2 x W 128-bit loads in flight per thread
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += U * stride) {
     float4 v[U][W];
@@ -118,7 +122,7 @@ peer_grad_allreduce_kernel(PeerTable pt, PeerGradTable gt, long long n4, int ran
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int r = 0; r < W; ++r)
-        if (i + u * stride < hi) v[u][r] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(gt.grad[r]) + i + u * stride);
+        if (i + u * stride < hi) v[u][r] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(gt.grad[r]) + off4 + i + u * stride);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i + u * stride >= hi) continue;
@@ -127,7 +131,7 @@ peer_grad_allreduce_kernel(PeerTable pt, PeerGradTable gt, long long n4, int ran
       for (int r = 1; r < W; ++r) { s.x += v[u][r].x; s.y += v[u][r].y; s.z += v[u][r].z; s.w += v[u][r].w; }
       s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
 #pragma unroll
-      for (int r = 0; r < W; ++r) st_relaxed_sys_f4(reinterpret_cast<float4*>(gt.grad[r]) + i + u * stride, s);
+      for (int r = 0; r < W; ++r) st_relaxed_sys_f4(reinterpret_cast<float4*>(gt.grad[r]) + off4 + i + u * stride, s);
     }
   }
   // last block of the grid: all slices of this rank are stored (fence + ticket) -> tell every peer, then wait for theirs
@@ -244,8 +248,9 @@ extern "C" int dig_peer_error(const int64_t* bases, int32_t world, int32_t rank,
 }
 
 extern "C" int dig_peer_grad_allreduce(const int64_t* bases, const int64_t* grad_bases, int32_t world, int32_t rank, int32_t channel,
-                                       int64_t epoch, int64_t n, int32_t blocks, void* stream) {
-  DIG_REQUIRE(bases && grad_bases && n > 0 && n % 4 == 0, "dig_peer_grad_allreduce: n must be a positive multiple of 4 (got %lld)", (long long)n);
+                                       int64_t epoch, int64_t offset, int64_t n, int32_t blocks, int32_t small_blocks, void* stream) {
+  DIG_REQUIRE(bases && grad_bases && n > 0 && n % 4 == 0 && offset >= 0 && offset % 4 == 0,
+              "dig_peer_grad_allreduce: offset and n must be multiples of 4 floats (got %lld, %lld)", (long long)offset, (long long)n);
   DIG_REQUIRE(rank >= 0 && rank < world && channel >= 0 && channel < kPeerChannels && epoch >= 1 && epoch < (1ll << 30),
               "dig_peer_grad_allreduce: bad rank/channel/epoch");
   PeerTable pt;
@@ -254,16 +259,22 @@ extern "C" int dig_peer_grad_allreduce(const int64_t* bases, const int64_t* grad
   for (int i = 0; i < kPeerMaxRanks; ++i) gt.grad[i] = i < world ? reinterpret_cast<float*>((uintptr_t)grad_bases[i]) : nullptr;
   for (int i = 0; i < world; ++i) DIG_REQUIRE(gt.grad[i] != nullptr && ((uintptr_t)gt.grad[i] & 15) == 0, "dig_peer_grad_allreduce: rank %d has no (16-byte aligned) mapped gradient buffer", i);
   if (blocks <= 0) blocks = num_sms();
-  const long long n4 = n / 4;
+  const long long n4 = n / 4, off4 = offset / 4;
   cudaStream_t s = (cudaStream_t)stream;
-  switch (world) {
-    case 2: peer_grad_allreduce_kernel<2><<<blocks, 512, 0, s>>>(pt, gt, n4, rank, channel, (uint32_t)epoch); break;
-    case 4: peer_grad_allreduce_kernel<4><<<blocks, 512, 0, s>>>(pt, gt, n4, rank, channel, (uint32_t)epoch); break;
-    case 8: peer_grad_allreduce_kernel<8><<<blocks, 512, 0, s>>>(pt, gt, n4, rank, channel, (uint32_t)epoch); break;
+  const uint32_t e = (uint32_t)epoch;
+#define DIG_PG(W, T, U) peer_grad_allreduce_kernel<W, T, U><<<blocks, T, 0, s>>>(pt, gt, off4, n4, rank, channel, e)
+  switch (world * 2 + (small_blocks ? 1 : 0)) {
+    case 4: DIG_PG(2, 512, 2); break;
+    case 5: DIG_PG(2, 128, 4); break;
+    case 8: DIG_PG(4, 512, 2); break;
+    case 9: DIG_PG(4, 128, 2); break;
+    case 16: DIG_PG(8, 512, 2); break;
+    case 17: DIG_PG(8, 128, 1); break;
     default:
       set_last_error("dig_peer_grad_allreduce: built for 2, 4 or 8 ranks (got %d)", world);
       return -1;
   }
+#undef DIG_PG
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -122,6 +122,7 @@ class PretrainStep:
         self._peer = None
         self._grad_flat = None
         self._grad_peer = None      # table of every rank's flat gradient buffer when it lives in IPC-mapped memory
+        self._comm_stream = None    # stream of the gradient exchanges that overlap the backward
         # The momentum branch (EMA update + no-grad forward) and the online branch are independent until the InfoNCE logits: they run
         # on two streams so that one branch's HBM-bound kernels (LayerNorm, BatchNorm, casts) fill in under the other's GEMMs.
         import os
@@ -664,6 +665,12 @@ class PretrainStep:
         self._sync_works = []
         self._sync_flat = flat if (sync is not None and world > 1) else None
         self._sync_peer = self._grad_peer is not None and flat is self._grad_flat and self._peer is not None   # else: NCCL segments
+        self._peer_pending = []
+        nb = len(self.model.encoder.blocks)
+        # DIG_PEER_GRAD_OVERLAP = k exchanges overlapped with the backward, issued when the upper 1/(k+1), 2/(k+1), ... of the encoder blocks
+        # are final (0: one exchange at the end)
+        k = max(0, min(int(os.environ.get("DIG_PEER_GRAD_OVERLAP", "3")), nb - 1))
+        self._peer_flush_keys = {"block%d" % (nb - (j * nb) // (k + 1)) for j in range(1, k + 1)}
         self._sync_group = sync.process_group if sync is not None else None
         Bf.zero_phase("bwd")
         g = Bf.get("bw.g", (M, d), F32)
@@ -724,17 +731,36 @@ class PretrainStep:
             w.wait()
         self._sync_works = []
         if self._sync_flat is not None and self._sync_peer:
-            # every gradient of this rank is final (main stream; the side stream's weight gradients were joined above)
-            pc = self._peer
-            call("dig_peer_grad_allreduce", pc.bases, self._grad_peer, pc.world, pc.rank, peer.CH_GRADS, pc.next_epoch(peer.CH_GRADS),
-                 self.grad_total, int(os.environ.get("DIG_PEER_GRAD_BLOCKS", "0")))
+            # every gradient of this rank is final (main stream; the side stream -- weight gradients, earlier exchanges -- was joined above)
+            if self._comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._comm_stream)     # exchanges of the channel stay stream-ordered
+            self._peer_flush(final=True)
         self.saved = None
         return [grads[n] for n in self.train_names]
 
     def _allreduce_segment(self, key, stream=None, after=None):
         """DigDataParallel: average one finished segment of the flat gradient buffer over the ranks (async NCCL all-reduce, issued on
         `stream` -- the side stream during the encoder backward -- after the event `after` recorded on the chain stream)."""
-        if self._sync_flat is None or self._sync_peer:
+        if self._sync_flat is None:
+            return
+        if self._sync_peer:
+            # peer-memory path: finished segments are collected and averaged in a few exchanges -- two from the side stream in the middle of
+            # the backward (blocks small enough to sit next to the resident GEMM CTAs), the rest in one full-width kernel at the end
+            self._peer_pending.append(key)
+            if key in self._peer_flush_keys:
+                # on a stream of its own (the exchange waits for the other ranks: it must not hold up the weight gradients queued behind it
+                # on the side stream), after everything queued so far on the chain stream and on the side stream
+                cur = torch.cuda.current_stream()
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(device=self.device)
+                comm = self._comm_stream
+                for st in (cur, stream):
+                    if st is not None:
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    self._peer_flush(final=False)
             return
         a, b = self.grad_seg[key]
         cur = torch.cuda.current_stream()
@@ -746,6 +772,30 @@ class PretrainStep:
             st.wait_event(after)
         with torch.cuda.stream(st):
             self._sync_works.append(dist.all_reduce(self._sync_flat[a:b], op=dist.ReduceOp.AVG, group=self._sync_group, async_op=True))
+
+
+def _peer_flush_impl(self, final):
+    """Average the pending (finished) segments of the flat gradient buffer over the ranks with dig_peer_grad_allreduce: one call per
+    contiguous range.  Every rank issues the same sequence (the segment order is a property of the model)."""
+    if not self._peer_pending:
+        return
+    rng = sorted(self.grad_seg[k] for k in self._peer_pending)
+    self._peer_pending = []
+    merged = [list(rng[0])]
+    for a, b in rng[1:]:
+        if a == merged[-1][1]:
+            merged[-1][1] = b
+        else:
+            merged.append([a, b])
+    pc = self._peer
+    for a, b in merged:
+        if a % 4 or (b - a) % 4:
+            raise ops.DigError("gradient segment [%d, %d) is not 16-byte aligned" % (a, b))
+        call("dig_peer_grad_allreduce", pc.bases, self._grad_peer, pc.world, pc.rank, peer.CH_GRADS, pc.next_epoch(peer.CH_GRADS), a, b - a,
+             int(os.environ.get("DIG_PEER_GRAD_BLOCKS", "0")) if final else 0, 0 if final else 1)
+
+
+PretrainStep._peer_flush = _peer_flush_impl
 
 
 class _PretrainFn(torch.autograd.Function):

@@ -157,13 +157,15 @@ int dig_bn_bwd_stats_allreduce(const float* dy, const float* x, const float* sta
 int dig_peer_l2norm_allgather(const int64_t* bases, int32_t world, int32_t rank, int32_t channel, int64_t epoch, const float* x,
                               float* local_copy, int64_t Q, int32_t C, int64_t key_table_bytes, void* stream);
 /* Gradient averaging of the data-parallel step (torch DistributedDataParallel's bucket all-reduce, R:391) over peer memory:
- * grad_bases[r] = device address of rank r's flat fp32 gradient buffer of n floats (this rank's own at [rank], the others
- * IPC-mapped; allocate with dig_peer_alloc).  Rank r reads the r-th slice of all `world` buffers over NVLink, adds them in
- * rank order, scales by 1/world and stores the result into all of them; when the kernel completes, this rank's whole buffer
- * holds the average (bit-identical on every rank).  world in {2,4,8}; blocks <= 0: one per SM.  `channel` must be used by
- * this exchange only (4).                                                                                                */
+ * grad_bases[r] = device address of rank r's flat fp32 gradient buffer (this rank's own at [rank], the others IPC-mapped;
+ * allocate with dig_peer_alloc).  The call averages the `n` floats starting at `offset` (both multiples of 4): rank r reads
+ * the r-th slice of that range from all `world` buffers over NVLink, adds them in rank order, scales by 1/world and stores the
+ * result into all of them; when the kernel completes, this rank's range holds the average (bit-identical on every rank).
+ * world in {2,4,8}; blocks <= 0: one per SM; small_blocks != 0: 128-thread blocks of <= 64 registers that fit next to a
+ * resident persistent GEMM / attention CTA (for exchanges overlapped with the backward).  Calls on `channel` (4, used by
+ * nothing else) must be stream-ordered and identical on every rank.                                                       */
 int dig_peer_grad_allreduce(const int64_t* bases, const int64_t* grad_bases, int32_t world, int32_t rank, int32_t channel,
-                            int64_t epoch, int64_t n, int32_t blocks, void* stream);
+                            int64_t epoch, int64_t offset, int64_t n, int32_t blocks, int32_t small_blocks, void* stream);
 
 /* elementwise fp32 -> bf16 (n % 4 == 0). */
 int dig_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);

@@ -21,8 +21,8 @@ def fill(seed):
     buf.copy_(torch.randn(n, device=dev, generator=g))
 
 
-def peer_ar(blocks):
-    ops.call("dig_peer_grad_allreduce", comm.bases, table, world, rank, peer.CH_GRADS, comm.next_epoch(peer.CH_GRADS), n, blocks)
+def peer_ar(blocks, small=0):
+    ops.call("dig_peer_grad_allreduce", comm.bases, table, world, rank, peer.CH_GRADS, comm.next_epoch(peer.CH_GRADS), 0, n, blocks, small)
 
 
 # correctness: average over ranks
@@ -55,6 +55,8 @@ def timeit(name, f, iters=10):
 
 for blocks in (148, 64, 32, 16, 8):
     timeit("peer grad all-reduce, %3d blocks" % blocks, lambda b=blocks: peer_ar(b))
+for blocks in (148, 296, 592):
+    timeit("peer grad all-reduce, %3d small blocks (128 thr)" % blocks, lambda b=blocks: peer_ar(b, 1))
 timeit("NCCL all_reduce (one call, 174 MB)", lambda: dist.all_reduce(buf, op=dist.ReduceOp.AVG))
 seg = n // 14 // 4 * 4
 timeit("NCCL all_reduce (14 segments)", lambda: [dist.all_reduce(buf[i * seg:(i + 1) * seg], op=dist.ReduceOp.AVG) for i in range(14)])
