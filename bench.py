@@ -114,12 +114,9 @@ def _cpu_reference_real_run(model_name, B, steps, warmup):
     M, E, U, AdamW = ref_shims.import_reference()
     created = False
     if not dist.is_initialized():          # contrastive_loss needs a group even at W = 1 (M:449-453)
-        import socket
-        s = socket.socket()
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-        s.close()
-        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+        # an in-process store: under torchrun a tcp:// rendezvous is redirected to the elastic agent's store (TORCHELASTIC_USE_AGENT_STORE)
+        # and a one-rank group of rank 0 alone would wait for it forever
+        dist.init_process_group("gloo", store=dist.HashStore(), rank=0, world_size=1)
         created = True
     try:
         model = ref_shims.create_reference_model(model_name, seed=0)

@@ -163,3 +163,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["metric"].startswith("pretrain text-crops/sec")
+
+
+def test_bench_reference_arm_under_torchrun_rank0_prints_and_the_others_exit():
+    """The driver launches the reference arm like the GPU arm (torchrun for N > 1): rank 0 alone runs it, and its one-rank process group
+    must not go through the elastic agent's store (a tcp:// rendezvous hung there)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(29800 + os.getpid() % 100), os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "0", "--cpu-batch", "2"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
