@@ -180,3 +180,59 @@ def test_bench_reference_arm_under_torchrun_rank0_prints_and_the_others_exit():
     assert len(lines) == 1
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+
+
+def test_peer_gradient_exchanges_cover_the_flat_buffer_once(monkeypatch):
+    """PretrainStep._allreduce_segment / _peer_flush on the peer-memory path: the segments the backward finalises (heads, blocks 11..0,
+    embed) are averaged in k overlapped exchanges (small co-resident blocks) plus one full-width exchange at the end, each a contiguous,
+    16-byte aligned range, together covering [0, total) exactly once, with consecutive epochs on the gradient channel."""
+    from dig_b200 import peer, pretrain_step
+
+    calls = []
+    monkeypatch.setattr(pretrain_step, "call", lambda name, *a: calls.append((name,) + a))
+
+    class Comm:
+        bases, world, rank = "bases", 8, 3
+
+        def __init__(self):
+            self.e = 0
+
+        def next_epoch(self, ch):
+            assert ch == peer.CH_GRADS
+            self.e += 1
+            return self.e
+
+    for k, want_mid in ((3, 3), (2, 2), (0, 0)):
+        calls.clear()
+        seg, off = {}, 0
+        for name, n in [("embed", 1000)] + [("block%d" % i, 400 + 8 * i) for i in range(12)] + [("heads", 2000)]:
+            seg[name] = (off, off + n)
+            off += n
+        st = pretrain_step.PretrainStep.__new__(pretrain_step.PretrainStep)
+        st.grad_seg, st._peer, st._grad_peer, st._peer_pending = seg, Comm(), "table", []
+        st._peer_flush_keys = {"block%d" % (12 - (j * 12) // (k + 1)) for j in range(1, k + 1)}
+        for key in ["heads"] + ["block%d" % i for i in reversed(range(12))] + ["embed"]:
+            st._peer_pending.append(key)
+            if key in st._peer_flush_keys:
+                st._peer_flush(final=False)
+        st._peer_flush(final=True)
+        assert all(c[0] == "dig_peer_grad_allreduce" for c in calls)
+        spans = sorted((c[7], c[7] + c[8]) for c in calls)
+        assert spans[0][0] == 0 and spans[-1][1] == off and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(c[7] % 4 == 0 and c[8] % 4 == 0 for c in calls)
+        assert [c[6] for c in calls] == list(range(1, len(calls) + 1))                 # epochs in issue order
+        assert sum(1 for c in calls if c[10] == 1) == want_mid and calls[-1][10] == 0   # small blocks in the middle, full width at the end
+        assert len(calls) == want_mid + 1
+
+
+def test_device_prefetch_passes_batches_through_in_order():
+    """engine._DevicePrefetch (CPU: no side stream): same items, same order, same length as the wrapped loader."""
+    import torch
+    from dig_b200.engine import _DevicePrefetch
+    items = [((torch.full((2,), float(i)), torch.zeros(1), torch.ones(1)), "text%d" % i, i) for i in range(5)]
+    feed = _DevicePrefetch(items, torch.device("cpu"))
+    assert len(feed) == 5
+    got = list(feed)
+    assert [g[1] for g in got] == ["text%d" % i for i in range(5)]
+    assert all(torch.equal(g[0][0], it[0][0]) for g, it in zip(got, items))
+    assert list(_DevicePrefetch([], torch.device("cpu"))) == []
