@@ -95,3 +95,71 @@ def train_one_epoch(model, criterion, data_loader, optimizer, device, epoch, los
     stats = {k: meter.global_avg for k, meter in metric_logger.meters.items()}
     stats.update({"max_accuracy": max_accuracy})
     return stats
+
+
+# ---- evaluation (reference engine_for_finetuning.py:212-285; metrics of evaluation_metric/metrics.py:14-96 restated on label ids) ----
+def _strings(ids, dataset):
+    """evaluation_metric/metrics.py:19-64 get_str_list for one id matrix: characters up to (not including) <EOS>, <UNKNOWN> dropped,
+    then only [0-9a-zA-Z] kept and lower-cased (_normalize_text)."""
+    import string
+    keep = set(string.digits + string.ascii_letters)
+    eos, unk = dataset.class_to_idx["EOS"], dataset.class_to_idx["UNKNOWN"]
+    out = []
+    for row in ids.tolist():
+        chars = []
+        for v in row:
+            if v == eos:
+                break
+            if v != unk:
+                chars.append(dataset.idx_to_class[v])
+        out.append("".join(c for c in "".join(chars) if c in keep).lower())
+    return out
+
+
+def word_accuracy(pred_ids, target, dataset):
+    """evaluation_metric.Accuracy (metrics.py:76-81): fraction of samples whose normalised strings are equal."""
+    p, t = _strings(pred_ids, dataset), _strings(target, dataset)
+    return sum(a == b for a, b in zip(p, t)) / max(len(p), 1)
+
+
+def recognition_fmeasure(pred_ids, target, dataset):
+    """evaluation_metric.recognition_f_measure (metrics.py:83-100): mean F-measure over the SETS of characters of prediction and target."""
+    fs = []
+    for pred, targ in zip(_strings(pred_ids, dataset), _strings(target, dataset)):
+        pc, tc = set(pred), set(targ)
+        right = float(len(pc & tc))
+        p, r = right / (len(pc) + 1e-5), right / (len(tc) + 1e-5)
+        fs.append(2 * p * r / (p + r + 1e-5))
+    return sum(fs) / max(len(fs), 1)
+
+
+@torch.no_grad()
+def evaluate(data_loader, model, device, args=None):
+    """Same contract as the reference's evaluate (engine_for_finetuning.py:212-285) for the tf_decoder model: eval mode (greedy decoding on
+    the fused kernels, dig_b200/finetune.py), the criterion applied to the decoder's step PROBABILITIES exactly as the reference does
+    (E-ft:240), word accuracy and the character-set F-measure; returns the meters' global averages."""
+    from .finetune import SeqCrossEntropyLoss
+    if getattr(args, "beam_width", 0):
+        raise NotImplementedError("beam search (models/decoder.py:252-330) is not built; evaluate with --beam_width 0")
+    criterion = SeqCrossEntropyLoss()
+    metric_logger = utils.MetricLogger(delimiter="  ")
+    header = "Test:"
+    model.eval()
+    for batch in metric_logger.log_every(data_loader, 10, header):
+        images, target, lens = batch[0], batch[1], batch[-1]
+        images = images.to(device, non_blocking=True)
+        target = target.to(device, non_blocking=True)
+        lens = lens.to(device, non_blocking=True)
+        output = model((images, target, lens))[0]
+        loss = criterion(output, target, lens)
+        pred_ids = output.argmax(-1)
+        dataset = data_loader.dataset
+        bs = images.shape[0]
+        metric_logger.update(loss=float(loss))
+        metric_logger.meters["acc"].update(word_accuracy(pred_ids.cpu(), target.cpu(), dataset), n=bs)
+        metric_logger.meters["recognition_fmeasure"].update(recognition_fmeasure(pred_ids.cpu(), target.cpu(), dataset), n=bs)
+    metric_logger.synchronize_between_processes()
+    print("* {} images, Acc {acc.global_avg:.4f} loss {losses.global_avg:.4f} Rec_fmeasure {rec_f.global_avg:.4f}".format(
+        metric_logger.meters["acc"].count, acc=metric_logger.meters["acc"], losses=metric_logger.meters["loss"],
+        rec_f=metric_logger.meters["recognition_fmeasure"]))
+    return {k: meter.global_avg for k, meter in metric_logger.meters.items()}

@@ -7,7 +7,7 @@ models/transformer_layer.py:47-118).  `FinetuneStep` sequences its training forw
 the pre-training path (dig_gemm, fused attention, LayerNorm kernels); every decoder Linear is a dig_gemm (q/k/v and the cross-attention
 k/v projections fused into one GEMM each); the T <= 32-query attention, the <BOS>-shifted embedding and SeqCrossEntropyLoss run in
 csrc/decoder.cu.  Built: training forward with every dropout / drop-path probability 0 (the README's 0.1 rates need RNG-matched dropout
-inside the fused kernels) and teacher forcing (`forward_train`); greedy / beam decoding (eval) is not built and raises.
+inside the fused kernels), teacher forcing (`forward_train`) in train mode and greedy decoding (`forward_test`) in eval mode; beam search raises.
 """
 import os
 
@@ -113,9 +113,13 @@ class DigRecModel(nn.Module):
         images, targets, tgt_lens = x
         if not images.is_cuda:
             raise RuntimeError("dig_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
-        if not self.training:
-            raise NotImplementedError("eval-mode decoding (forward_test / beam_search, models/decoder.py:224-330) is not built")
         step = self._pipeline()
+        if not self.training:
+            # eval mode (model_builder.py:137-139 drops the targets): greedy decoding, TFDecoder.forward_test (decoder.py:224-250)
+            if getattr(self, "beam_width", 0):
+                raise NotImplementedError("beam search (models/decoder.py:252-330) is not built; evaluate with --beam_width 0")
+            probs, maps, _ = step.greedy_decode(images, need_maps=bool(getattr(self, "return_attn_maps", False)))
+            return probs, None, None, maps
         params = step.trainable_params()
         if torch.is_grad_enabled():
             logits = _FinetuneFn.apply(step, images, targets, tgt_lens, *params)
@@ -214,7 +218,32 @@ class FinetuneStep(PretrainStep):
         self.mask_zero = {}
 
     # ------------------------------------------------------------------ forward (model_builder.py:124-169, decoder.py:180-222)
-    def forward(self, images, targets, tgt_lens, need_maps=False):
+    def greedy_decode(self, images, need_maps=False, force_tokens=None):
+        """RecModel.forward in eval mode with beam_width 0 = TFDecoder.forward_test (models/decoder.py:224-250): max_seq_len decoder passes
+        over the <BOS>-shifted sequence decoded so far (tgt_lens = step + 1), softmax of the classifier output at position `step`, its
+        arg-max fed back.  The encoder and linear_norm run once; every step reuses their output (the decoder's memory).
+        -> (probabilities fp32 [B, T, C], head-averaged cross-attention maps of the last layer [B, T, 256] or None, tokens int64 [B, T]).
+        force_tokens [B, T] (tests only) replaces the fed-back arg-max."""
+        B, T, dev = images.shape[0], int(self.model.decoder.max_seq_len), self.device
+        toks = torch.zeros(B, T, dtype=torch.int64, device=dev)           # position t feeds the query at t + 1 (decoder.py:247)
+        out = torch.zeros(B, T, dtype=torch.int64, device=dev)
+        probs = torch.empty(B, T, self.C, dtype=F32, device=dev)
+        maps = torch.empty(B, T, TOK, dtype=F32, device=dev) if need_maps else None
+        with torch.no_grad():
+            for t in range(T):
+                lens = torch.full((B,), t + 1, dtype=torch.int64, device=dev)
+                logits = self.forward(images, toks, lens, need_maps=need_maps, reuse_memory=t > 0)
+                p = torch.softmax(logits[:, t].float(), dim=-1)
+                probs[:, t] = p
+                out[:, t] = p.argmax(-1)
+                toks[:, t] = out[:, t] if force_tokens is None else force_tokens[:, t].to(dev)
+                if need_maps:
+                    maps[:, t] = self.last_maps[:, t]
+        self.saved = None          # nothing of these passes may be back-propagated
+        return probs, maps, out
+
+    def forward(self, images, targets, tgt_lens, need_maps=False, reuse_memory=False):
+        """reuse_memory (greedy decoding): skip the encoder / linear_norm and decode against the memory of the previous call."""
         model, Bf, dev = self.model, self.bufs, self.device
         N_, S_ = self._named, self.shadow
         B, T = targets.shape
@@ -227,23 +256,26 @@ class FinetuneStep(PretrainStep):
             self._mt("dig_mt_cast_bf16", self.tab_cast_online)
             self._cast_state = state
         self._mt("dig_mt_copy_f32", self.tab_qkv_bias["encoder."])
-        images = images.to(F32).contiguous()
         targets = targets.to(dev, torch.int64).contiguous()
         tgt_lens = tgt_lens.to(dev, torch.int64).contiguous()
-        mask_u8 = self.mask_zero.get(M)
-        if mask_u8 is None:
-            mask_u8 = self.mask_zero[M] = torch.zeros(M, dtype=torch.uint8, device=dev)
         W = self._enc_weights("encoder.")
-        x, sv_enc = self._encoder_fwd(W, images, mask_u8, "f.", save=True)
-        # final encoder norm (V:104) and linear_norm (model_builder.py:86-89, :146)
-        encn = Bf.get("f.encn", (M, d), BF16)
-        me, re = Bf.get("f.me", (M,), F32), Bf.get("f.re", (M,), F32)
-        self._ln(x, N_["encoder.norm.weight"], N_["encoder.norm.bias"], encn, me, re, eps=model.encoder.norm.eps)
-        lpre = Bf.get("f.lpre", (M, dm), F32)
-        ops.gemm(encn, S_["linear_norm.0.weight"], lpre, bias=N_["linear_norm.0.bias"])
         mem = Bf.get("f.mem", (M, dm), BF16)
-        ml, rl = Bf.get("f.ml", (M,), F32), Bf.get("f.rl", (M,), F32)
-        self._ln(lpre, N_["linear_norm.1.weight"], N_["linear_norm.1.bias"], mem, ml, rl, eps=model.linear_norm[1].eps)
+        if reuse_memory:
+            sv_enc = x = encn = me = re = lpre = ml = rl = None
+        else:
+            images = images.to(F32).contiguous()
+            mask_u8 = self.mask_zero.get(M)
+            if mask_u8 is None:
+                mask_u8 = self.mask_zero[M] = torch.zeros(M, dtype=torch.uint8, device=dev)
+            x, sv_enc = self._encoder_fwd(W, images, mask_u8, "f.", save=True)
+            # final encoder norm (V:104) and linear_norm (model_builder.py:86-89, :146)
+            encn = Bf.get("f.encn", (M, d), BF16)
+            me, re = Bf.get("f.me", (M,), F32), Bf.get("f.re", (M,), F32)
+            self._ln(x, N_["encoder.norm.weight"], N_["encoder.norm.bias"], encn, me, re, eps=model.encoder.norm.eps)
+            lpre = Bf.get("f.lpre", (M, dm), F32)
+            ops.gemm(encn, S_["linear_norm.0.weight"], lpre, bias=N_["linear_norm.0.bias"])
+            ml, rl = Bf.get("f.ml", (M,), F32), Bf.get("f.rl", (M,), F32)
+            self._ln(lpre, N_["linear_norm.1.weight"], N_["linear_norm.1.bias"], mem, ml, rl, eps=model.linear_norm[1].eps)
         # decoder input: <BOS>-shifted target embedding + position table (decoder.py:173-178, :212-214)
         xd = Bf.get("d.x0", (Md, dm), F32)
         call("dig_embed_pos_fwd", targets, N_["decoder.trg_word_emb.weight"], model.decoder.position_enc.position_table, xd, B, T, dm,

@@ -76,6 +76,42 @@ def rec_forward(sd, images, targets, tgt_lens, heads, n_head=8, n_layers=6, num_
     return Fn.linear(x, sd["decoder.classifier.weight"], sd["decoder.classifier.bias"]), maps
 
 
+def encode_memory(sd, images, heads):
+    """model_builder.py:126-146: encoder (+ final norm) -> linear_norm: the decoder's memory [B, 256, d_model]."""
+    enc = encoder_forward(sd, images, heads)
+    mem = Fn.linear(enc, sd["linear_norm.0.weight"], sd["linear_norm.0.bias"])
+    return Fn.layer_norm(mem, (mem.shape[-1],), sd["linear_norm.1.weight"], sd["linear_norm.1.bias"], DEC_LN_EPS)
+
+
+def greedy_decode(sd, images, heads, n_head=8, n_layers=6, num_classes=97, max_len=25, force_tokens=None):
+    """RecModel.forward in eval mode with beam_width 0 = TFDecoder.forward_test (models/decoder.py:224-250): the target sequence starts as
+    [<BOS>, 0, 0, ...] (max_len + 1 positions); step t runs the whole decoder with tgt_lens = t + 1, takes softmax(classifier(output[:, t])),
+    and writes its arg-max into position t + 1.  Returns (probabilities [B, max_len, C], cross-attention maps [B, max_len, 256], tokens
+    [B, max_len]).  force_tokens [B, max_len] (tests only) replaces the fed-back arg-max."""
+    mem = encode_memory(sd, images, heads)
+    B, dev = images.shape[0], images.device
+    T1 = max_len + 1
+    seq = torch.zeros(B, T1, dtype=torch.long, device=dev)
+    seq[:, 0] = num_classes                                                   # start_idx (decoder.py:229)
+    probs, maps_out, toks = [], [], []
+    pos = sd["decoder.position_enc.position_table"][:, :T1]
+    for step in range(max_len):
+        lens = torch.full((B,), step + 1, dtype=torch.long, device=dev)
+        x = Fn.embedding(seq, sd["decoder.trg_word_emb.weight"]) + pos
+        mask = self_attention_mask(lens, T1, dev)
+        maps = None
+        for l in range(n_layers):
+            x, maps = decoder_layer(sd, "decoder.layer_stack.%d." % l, x, mem, mask, n_head)
+        x = Fn.layer_norm(x, (x.shape[-1],), sd["decoder.layer_norm.weight"], sd["decoder.layer_norm.bias"], DEC_FINAL_LN_EPS)
+        p = Fn.softmax(Fn.linear(x[:, step], sd["decoder.classifier.weight"], sd["decoder.classifier.bias"]), dim=-1)
+        probs.append(p)
+        maps_out.append(maps[:, step])
+        nxt = p.argmax(-1) if force_tokens is None else force_tokens[:, step].to(dev)
+        toks.append(p.argmax(-1))
+        seq[:, step + 1] = nxt
+    return torch.stack(probs, 1), torch.stack(maps_out, 1), torch.stack(toks, 1)
+
+
 def seq_cross_entropy(logits, targets, tgt_lens):
     """loss/seqCrossEntropyLoss.py:47-63 with sample_normalize=True: sum over valid positions of -log p[target] / batch size."""
     B, T, C = logits.shape

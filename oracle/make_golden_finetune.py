@@ -35,7 +35,12 @@ def reference_step(model_name, B, seed_model=0, seed_data=1):
     loss = crit(out[0], tgt, lens)
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
-    return dict(model=model_name, B=B, seed_model=seed_model, seed_data=seed_data, loss=float(loss), logits=out[0].detach().clone(),
+    # eval mode, beam_width 0: TFDecoder.forward_test (greedy decoding, decoder.py:224-250) of the same images
+    with torch.no_grad():
+        ev = model.eval()((img, tgt, lens))
+    model.train()
+    return dict(eval_probs=ev[0].detach().clone(), eval_maps=ev[3].detach().clone(),
+                model=model_name, B=B, seed_model=seed_model, seed_data=seed_data, loss=float(loss), logits=out[0].detach().clone(),
                 attn_maps=out[3].detach().clone(), state_keys=[(k, tuple(v.shape), str(v.dtype)) for k, v in sd0.items()],
                 param_checksum={k: float(v.double().sum()) for k, v in sd0.items() if v.dtype.is_floating_point},
                 grad_norms={n: float(g.norm()) for n, g in grads.items()},

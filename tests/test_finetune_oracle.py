@@ -41,3 +41,18 @@ def test_finetune_oracle_reproduces_reference_golden(tag):
         assert float(grads[n].norm()) == pytest.approx(ref, rel=2e-3, abs=1e-7), n
     for n, ref in g["grad_samples"].items():
         assert torch.allclose(grads[n].flatten()[:64], ref, atol=1e-4, rtol=2e-3), n
+
+
+@pytest.mark.parametrize("tag", ["tiny_b3", "small_b4"])
+def test_greedy_decoding_restatement_reproduces_reference_eval_mode(tag):
+    """RecModel.forward in eval mode (TFDecoder.forward_test, models/decoder.py:224-250): step probabilities and cross-attention maps of the
+    restated greedy decoding against the unmodified reference's (fixture written by oracle/make_golden_finetune.py)."""
+    g = torch.load(os.path.join(GOLD, "ref_finetune_%s.pt" % tag), weights_only=False)
+    sd = _reference_state(g)
+    img, _, _ = FR.synthetic_batch(g["B"], seed=g["seed_data"])
+    with torch.no_grad():
+        probs, maps, toks = FR.greedy_decode(sd, img, HEADS[g["model"]])
+    assert probs.shape == g["eval_probs"].shape == (g["B"], 25, 97)
+    assert torch.allclose(probs, g["eval_probs"], atol=2e-6) and torch.allclose(maps, g["eval_maps"], atol=1e-5)
+    assert torch.equal(toks, g["eval_probs"].argmax(-1))
+    assert torch.allclose(probs.sum(-1), torch.ones(g["B"], 25), atol=1e-5)

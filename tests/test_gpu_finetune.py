@@ -124,3 +124,57 @@ def test_finetune_train_one_epoch_learns():
                           start_steps=12, num_training_steps_per_epoch=12, update_freq=1, args=args)
     assert {"loss", "class_acc", "loss_scale", "lr", "min_lr", "weight_decay", "grad_norm", "max_accuracy"} <= set(st1)
     assert st1["loss"] < st0["loss"] and all(v == v for v in st1.values() if v is not None)
+
+
+class _ToyDataset:
+    """class_to_idx / idx_to_class of dataset_lmdb.py's 94 characters + EOS / PADDING / UNKNOWN."""
+
+    def __init__(self):
+        import string
+        voc = list(string.digits + string.ascii_lowercase + string.ascii_uppercase + string.punctuation) + ["EOS", "PADDING", "UNKNOWN"]
+        self.class_to_idx = {c: i for i, c in enumerate(voc)}
+        self.idx_to_class = {i: c for i, c in enumerate(voc)}
+
+
+@pytest.mark.parametrize("tag", ["tiny_b3", "small_b4"])
+def test_greedy_decoding_matches_reference_eval_mode(tag):
+    """Eval mode = TFDecoder.forward_test (decoder.py:224-250).  (a) With the reference's own fed-back tokens forced, the step probabilities
+    equal the fixture of the unmodified reference; (b) the free-running decode is self-consistent: teacher-forcing its tokens through the
+    training forward reproduces the same distributions at every position; (c) RecModel's eval-mode return tuple."""
+    from oracle import finetune_restatement as FR
+    g = torch.load(os.path.join(GOLD, "ref_finetune_%s.pt" % tag), weights_only=False)
+    model = _model(g["model"]).cuda()
+    img, tgt, lens = FR.synthetic_batch(g["B"], seed=g["seed_data"])
+    step = model._pipeline()
+    ref_tokens = g["eval_probs"].argmax(-1)
+    probs, maps, _ = step.greedy_decode(img.cuda(), need_maps=True, force_tokens=ref_tokens.cuda())
+    assert torch.allclose(probs.cpu(), g["eval_probs"], atol=2e-3, rtol=5e-2)
+    assert torch.allclose(maps.cpu(), g["eval_maps"], atol=2e-3)
+    model.eval()
+    with torch.no_grad():
+        out = model((img.cuda(), tgt.cuda(), lens.cuda()))
+    assert out[1] is None and out[2] is None and tuple(out[0].shape) == (g["B"], 25, 97)
+    assert torch.allclose(out[0].sum(-1), torch.ones(g["B"], 25, device="cuda"), atol=1e-4)
+    toks = out[0].argmax(-1)
+    model.train()
+    with torch.no_grad():
+        logits = model((img.cuda(), toks, torch.full((g["B"],), 25, device="cuda")))[0]
+    assert torch.allclose(torch.softmax(logits.float(), -1), out[0], atol=1e-4)
+
+
+def test_finetune_evaluate_contract():
+    from oracle import finetune_restatement as FR
+    from dig_b200.engine_finetune import evaluate, recognition_fmeasure, word_accuracy
+    ds = _ToyDataset()
+    t = torch.tensor([[10, 11, 94, 95, 95], [1, 96, 2, 94, 95]])          # "ab<EOS>", "1<UNK>2<EOS>"
+    assert word_accuracy(t.clone(), t, ds) == 1.0 and recognition_fmeasure(t.clone(), t, ds) == pytest.approx(1.0, abs=1e-4)
+    p = torch.tensor([[10, 12, 94, 0, 0], [1, 2, 94, 95, 95]])            # "ac" vs "ab": wrong; "12" vs "12" (UNKNOWN dropped): right
+    assert word_accuracy(p, t, ds) == 0.5
+    model = _model("simmim_vit_tiny_patch4_32x128").cuda()
+    img, tgt, lens = FR.synthetic_batch(6, seed=5)
+
+    class Loader(list):
+        dataset = ds
+    stats = evaluate(Loader([(img, tgt, lens)] * 2), model, torch.device("cuda"), args=types.SimpleNamespace(beam_width=0))
+    assert {"loss", "acc", "recognition_fmeasure"} <= set(stats) and all(v == v for v in stats.values())
+    assert 0.0 <= stats["acc"] <= 1.0 and not model.training
