@@ -164,24 +164,49 @@ infonce_rows_kernel(float* __restrict__ logits, int Q, int Nk, long long label_o
 // loss[0] += sum (pred - target)^2 / numel ; dpred = 2 (pred - target) / numel
 // One thread per (row, p1): the 12 consecutive prediction columns (p2, c) of one patch line = three 128-bit loads of pred, three 128-bit
 // loads of the image (the four p2 pixels of each colour plane are contiguous and 16-byte aligned), three 128-bit stores of dpred.
+// NORM (normlize_target=True, E:89-94): every colour plane of a patch is standardised over its 16 pixels first -- mean and UNBIASED
+// variance, target = (x - mean) / (sqrt(var) + 1e-6).  The four lines of a patch sit in four adjacent lanes: two xor-shuffles per sum.
+template <bool NORM>
 __global__ void __launch_bounds__(256)
 masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ images, const int* __restrict__ idx, float* __restrict__ loss,
                   float* __restrict__ dpred, long long n_rows) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const float inv_numel = 1.0f / (float)(n_rows * 48);
   float e = 0.f;
-  if (i < n_rows * 4) {
-    const long long r = i >> 2;
-    const int p1 = (int)(i & 3);
+  const bool active = i < n_rows * 4;       // whole groups of four lanes are active or not (n_rows * 4 is a multiple of 4)
+  float t[3][4] = {};
+  long long r = 0;
+  int p1 = 0;
+  if (active) {
+    r = i >> 2;
+    p1 = (int)(i & 3);
     const int tok_row = idx[r];
     const long long b = tok_row >> 8;
     const int tok = tok_row & 255, ph = tok >> 5, pw = tok & 31;
-    float t[3][4];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(images + ((b * 3 + c) * 32 + ph * 4 + p1) * 128 + pw * 4));
       t[c][0] = v.x * 0.5f + 0.5f; t[c][1] = v.y * 0.5f + 0.5f; t[c][2] = v.z * 0.5f + 0.5f; t[c][3] = v.w * 0.5f + 0.5f;
     }
+  }
+  if (NORM) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s = t[c][0] + t[c][1] + t[c][2] + t[c][3];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const float mean = s * (1.0f / 16.0f);
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { t[c][k] -= mean; q += t[c][k] * t[c][k]; }
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      const float inv = 1.0f / (sqrtf(q * (1.0f / 15.0f)) + 1e-6f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[c][k] *= inv;
+    }
+  }
+  if (active) {
     const float* pr = pred + r * 48 + p1 * 12;
     float d[12];
 #pragma unroll
@@ -274,10 +299,11 @@ extern "C" int dig_infonce_rows(float* logits, int32_t Q, int32_t Nk, int64_t la
 }
 
 extern "C" int dig_masked_mse(const float* pred, const float* images, const int32_t* idx, float* loss, float* dpred, int64_t n_rows,
-                              void* stream) {
+                              int32_t normalize_target, void* stream) {
   DIG_REQUIRE(pred && images && idx && loss && n_rows > 0, "dig_masked_mse: bad arguments");
   DIG_REQUIRE(((((uintptr_t)pred) | ((uintptr_t)images) | ((uintptr_t)dpred)) & 15) == 0, "dig_masked_mse: pred, images and dpred must be 16-byte aligned");
-  masked_mse_kernel<<<(int)((n_rows * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, images, idx, loss, dpred, n_rows);
+  if (normalize_target) masked_mse_kernel<true><<<(int)((n_rows * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, images, idx, loss, dpred, n_rows);
+  else masked_mse_kernel<false><<<(int)((n_rows * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, images, idx, loss, dpred, n_rows);
   DIG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -21,12 +21,12 @@ from .ops import call
 
 class _MaskedPixelMSE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, images, idx):
+    def forward(ctx, pred, images, idx, normalize_target=False):
         n_rows = idx.numel()
         p = pred.reshape(n_rows, 48).contiguous()
         loss = torch.zeros(1, dtype=torch.float32, device=pred.device)
         dpred = torch.empty_like(p)
-        call("dig_masked_mse", p, images, idx, loss, dpred, n_rows)
+        call("dig_masked_mse", p, images, idx, loss, dpred, n_rows, int(bool(normalize_target)))
         ctx.save_for_backward(dpred)
         ctx.shape = pred.shape
         return loss.reshape(())
@@ -36,19 +36,20 @@ class _MaskedPixelMSE(torch.autograd.Function):
         (dpred,) = ctx.saved_tensors
         out = torch.empty_like(dpred)
         call("dig_scale_by_device_scalar", dpred, g.reshape(1).to(torch.float32).contiguous(), out, dpred.numel())
-        return out.view(ctx.shape), None, None
+        return out.view(ctx.shape), None, None, None
 
 
-def masked_pixel_mse(pred, images, mask_view0):
+def masked_pixel_mse(pred, images, mask_view0, normalize_target=False):
     """F.mse_loss(pred, patchify(unnormalise(images))[mask]) (E:85-111,141).  pred fp32 [B,n,48]; images fp32 [B,3,32,128]
-    normalised with mean=std=0.5; mask_view0 bool/uint8 [B,256] with exactly n set positions per sample."""
+    normalised with mean=std=0.5; mask_view0 bool/uint8 [B,256] with exactly n set positions per sample.  normalize_target: the
+    per-patch standardised target of E:89-94 (`normlize_target=True`)."""
     B, n = pred.shape[0], pred.shape[1]
     if not pred.is_cuda:
         raise ops.DigError("masked_pixel_mse runs on CUDA tensors only")
     idx = torch.empty(B * n, dtype=torch.int32, device=pred.device)
     err = torch.zeros(1, dtype=torch.int32, device=pred.device)
     call("dig_mask_to_index", mask_view0.to(torch.uint8).contiguous(), idx, err, B, n)      # always writes B*n in-bounds indices
-    loss = _MaskedPixelMSE.apply(pred, images.contiguous(), idx)
+    loss = _MaskedPixelMSE.apply(pred, images.contiguous(), idx, normalize_target)
     loss._dig_mask_err = err      # device flag: some sample did not have exactly n masked patches (train_one_epoch reads it back)
     return loss
 
@@ -102,9 +103,6 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
                     start_steps=None, lr_schedule_values=None, wd_schedule_values=None, momentum_schedule=None, args=None):
     """Same contract as E:26-204.  `teacher_model`, `teacher_model_without_ddp`, `word_data_loader` and
     `momentum_schedule` are accepted and unused, exactly as in the reference."""
-    if normlize_target:
-        raise NotImplementedError("normlize_target=True (per-patch normalised targets, E:89-94) is not built; the README "
-                                  "configuration runs with the raw-pixel target (run_mae_pretraining_moco.py:90 default False)")
     if patch_size != 4:
         raise ops.DigError("patch_size must be 4 (pretrain_*_patch4_32x128), got %r" % (patch_size,))
     model.train()
@@ -184,7 +182,7 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
 
         out = model(images, aug_images, mask, moco_m, args.only_mim_on_ori_img)
         contra = out["contra_loss"]
-        loss_pixel = masked_pixel_mse(out["vis_out"][0], images, mask[:, 0])
+        loss_pixel = masked_pixel_mse(out["vis_out"][0], images, mask[:, 0], normalize_target=bool(normlize_target))
         loss = contra * float(w[step]) + loss_pixel * float(args.loss_weight_pixel)
 
         optimizer.zero_grad()

@@ -208,9 +208,11 @@ int dig_sgemm_f32(const float* A, const float* B, float* C, int32_t M, int32_t N
  * result[1]/[2] += top-1/top-5 accuracy in percent; logits are overwritten with d loss / d (q.k^T).    */
 int dig_infonce_rows(float* logits, int32_t Q, int32_t Nk, int64_t label_offset, float T, float* result, void* stream);
 /* Masked-pixel MSE (E:85-111 target build + E:141 F.mse_loss): pred fp32 [n_rows,48]; idx[r] = b*256 + token of view 0;
- * images fp32 [B,3,32,128] normalised with mean=std=0.5; loss[0] += mse; dpred (may be NULL) = d mse / d pred. */
+ * images fp32 [B,3,32,128] normalised with mean=std=0.5; loss[0] += mse; dpred (may be NULL) = d mse / d pred.
+ * normalize_target != 0: the `normlize_target` branch (E:89-94) -- every colour plane of a patch is standardised over its 16
+ * pixels (mean, unbiased variance, (x - mean) / (sqrt(var) + 1e-6)) before the comparison.                                */
 int dig_masked_mse(const float* pred, const float* images, const int32_t* idx, float* loss, float* dpred, int64_t n_rows,
-                   void* stream);
+                   int32_t normalize_target, void* stream);
 int dig_scale_by_device_scalar(const float* x, const float* s, float* y, int64_t n, void* stream);
 
 /* ---- fine-tuning step: transformer decoder pieces ----------------------------------------------------

@@ -252,14 +252,18 @@ def moco_vit_forward(sd, image, aug_image, vis_mask_pos, m, heads, T=0.2, num_wi
     return out
 
 
-def build_targets(images, mask_bvn, only_mim_on_ori_img=True, patch_size=PATCH):
-    """E:83-111 (normlize_target False): un-normalise, patchify '(p1 p2 c)', masked gather.
+def build_targets(images, mask_bvn, only_mim_on_ori_img=True, patch_size=PATCH, normalize_target=False):
+    """E:83-111: un-normalise, patchify '(p1 p2 c)', masked gather; normalize_target = the `normlize_target` branch (E:89-94): every
+    colour plane of a patch standardised over its p1*p2 pixels (mean, unbiased variance, + 1e-6 on the standard deviation).
     mask_bvn: bool [B, num_view, 256] (already zeroed for view 1 if only_mim_on_ori_img).
     Returns list of [B, n_masked, 48]."""
     unnorm = images * 0.5 + 0.5
     B, C, H, W = unnorm.shape
     h, w = H // patch_size, W // patch_size
-    p = unnorm.reshape(B, C, h, patch_size, w, patch_size).permute(0, 2, 4, 3, 5, 1)
+    p = unnorm.reshape(B, C, h, patch_size, w, patch_size).permute(0, 2, 4, 3, 5, 1)            # b h w p1 p2 c
+    if normalize_target:
+        sq = p.reshape(B, h * w, patch_size * patch_size, C)                                   # 'b (h w) (p1 p2) c'
+        p = (sq - sq.mean(dim=-2, keepdim=True)) / (sq.var(dim=-2, unbiased=True, keepdim=True).sqrt() + 1e-6)
     patches = p.reshape(B, h * w, patch_size * patch_size * C)
     views = 1 if only_mim_on_ori_img else mask_bvn.shape[1]
     return [patches[mask_bvn[:, i, :]].reshape(B, -1, patches.shape[-1]) for i in range(views)]

@@ -348,6 +348,16 @@ def test_contrastive_and_pixel_losses(ops):
     (out * 3.0).backward()
     assert float(out) == pytest.approx(float(ref), rel=1e-5)
     assert torch.allclose(p2.grad, 3.0 * pred.grad, atol=1e-8, rtol=1e-4)
+    # the `normlize_target=True` branch (E:89-94): per-patch, per-colour standardised targets
+    tgt_n = R.build_targets(img, mk, normalize_target=True)[0].cuda()
+    pred_n = pred.detach().clone().requires_grad_(True)
+    ref_n = torch.nn.functional.mse_loss(pred_n, tgt_n)
+    ref_n.backward()
+    p3 = pred.detach().clone().requires_grad_(True)
+    out_n = masked_pixel_mse(p3, img.cuda(), mk[:, 0].cuda(), normalize_target=True)
+    out_n.backward()
+    assert float(out_n) == pytest.approx(float(ref_n), rel=2e-5) and abs(float(out_n) - float(out)) > 1e-3
+    assert torch.allclose(p3.grad, pred_n.grad, atol=1e-7, rtol=1e-3)
 
 
 def test_multi_tensor_kernels(ops):

@@ -131,6 +131,13 @@ def test_train_one_epoch_contract_and_learning():
                              patch_size=4, normlize_target=False, start_steps=12, lr_schedule_values=lr_sched, args=args)
     assert stats1["loss_pixel"] < stats0["loss_pixel"]          # the same batch is being fitted
     assert all(v == v for v in stats1.values())
+    # normlize_target=True (E:89-94): per-patch standardised pixel targets (unit scale instead of ~0.08: a larger, still falling loss)
+    stats2 = train_one_epoch(model, None, None, loader, None, opt, torch.device("cuda"), 1, NativeScalerWithGradNormCount(), max_norm=None,
+                             patch_size=4, normlize_target=True, start_steps=12, lr_schedule_values=lr_sched, args=args)
+    stats3 = train_one_epoch(model, None, None, loader, None, opt, torch.device("cuda"), 1, NativeScalerWithGradNormCount(), max_norm=None,
+                             patch_size=4, normlize_target=True, start_steps=12, lr_schedule_values=lr_sched, args=args)
+    assert stats2["loss_pixel"] > 5 * stats1["loss_pixel"] and stats3["loss_pixel"] < stats2["loss_pixel"]
+    assert all(v == v for v in stats3.values())
 
 
 def test_state_dict_survives_device_move_and_reload():

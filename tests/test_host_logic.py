@@ -49,10 +49,14 @@ def test_scaler_state_has_scale():
 
 
 def test_engine_rejects_unbuilt_paths():
+    from dig_b200 import ops
     from dig_b200.engine import train_one_epoch
-    with pytest.raises(NotImplementedError):
-        train_one_epoch(torch.nn.Linear(1, 1), None, None, [], None, None, "cpu", 0, None, normlize_target=True, patch_size=4,
+    with pytest.raises(ops.DigError):          # only the patch4 models are built
+        train_one_epoch(torch.nn.Linear(1, 1), None, None, [], None, None, "cpu", 0, None, normlize_target=False, patch_size=16,
                         args=types.SimpleNamespace(num_view=2))
+    with pytest.raises(ops.DigError):          # the README runs two views
+        train_one_epoch(torch.nn.Linear(1, 1), None, None, [], None, None, "cpu", 0, None, normlize_target=True, patch_size=4,
+                        args=types.SimpleNamespace(num_view=1))
 
 
 def _worker(rank, world, port, q):

@@ -66,6 +66,24 @@ def test_decoder_on_gathered_rows_equals_reference_order():
     assert torch.allclose(full, first, atol=1e-6)
 
 
+def test_normalised_targets_equal_the_reference_statement():
+    """E:89-94 (`normlize_target=True`) written literally with einops, against R.build_targets(normalize_target=True)."""
+    from einops import rearrange
+    torch.manual_seed(4)
+    images = torch.rand(3, 3, 32, 128) * 2 - 1
+    mask = torch.zeros(3, 2, 256, dtype=torch.bool)
+    for b in range(3):
+        mask[b, 0, torch.randperm(256)[:179]] = True
+    unnorm = images * 0.5 + 0.5
+    sq = rearrange(unnorm, "b c (h p1) (w p2) -> b (h w) (p1 p2) c", p1=4, p2=4)
+    norm = (sq - sq.mean(dim=-2, keepdim=True)) / (sq.var(dim=-2, unbiased=True, keepdim=True).sqrt() + 1e-6)
+    want = rearrange(norm, "b n p c -> b n (p c)")[mask[:, 0]].reshape(3, -1, 48)
+    got = R.build_targets(images, mask, True, normalize_target=True)[0]
+    assert torch.equal(got, want)
+    plain = rearrange(unnorm, "b c (h p1) (w p2) -> b (h w) (p1 p2 c)", p1=4, p2=4)[mask[:, 0]].reshape(3, -1, 48)
+    assert torch.equal(R.build_targets(images, mask, True)[0], plain)
+
+
 def test_adamw_matches_torch():
     """custom_optim/_functional.py:115-140 restated == torch.optim.AdamW (same decoupled rule)."""
     torch.manual_seed(0)
