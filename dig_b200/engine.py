@@ -182,7 +182,10 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
 
         out = model(images, aug_images, mask, moco_m, args.only_mim_on_ori_img)
         contra = out["contra_loss"]
-        loss_pixel = masked_pixel_mse(out["vis_out"][0], images, mask[:, 0], normalize_target=bool(normlize_target))
+        # E:137-141: every masked view against the patches of the ORIGINAL image (E:83-111 builds all labels from `images`), 1/num_view each
+        per_view = [masked_pixel_mse(v, images, mask[:, i], normalize_target=bool(normlize_target)) for i, v in enumerate(out["vis_out"])]
+        loss_pixel = per_view[0] if len(per_view) == 1 else sum(per_view) * (1.0 / len(per_view))
+        loss_pixel._dig_mask_err = sum(lp._dig_mask_err for lp in per_view)
         loss = contra * float(w[step]) + loss_pixel * float(args.loss_weight_pixel)
 
         optimizer.zero_grad()

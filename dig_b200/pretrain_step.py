@@ -477,8 +477,6 @@ class PretrainStep:
         world, rank = _world()
         if vis_mask_pos.dim() != 3 or vis_mask_pos.shape[0] != Bsz or vis_mask_pos.shape[-1] != TOK:
             raise ops.DigError("vis_mask_pos must be [B, num_view, 256], got %s" % (tuple(vis_mask_pos.shape),))
-        if not only_mim_on_ori_img:
-            raise ops.DigError("only_mim_on_ori_img=False is not built (README.md:75 runs with --only_mim_on_ori_img 1)")
         if vis_mask_pos.shape[1] != 2:
             raise ops.DigError("num_view must be 2 (README.md:66), got %d" % vis_mask_pos.shape[1])
         self._check_mask_err()
@@ -495,12 +493,15 @@ class PretrainStep:
         mask_u8.view(2, Bsz, TOK).copy_(vis_mask_pos.permute(1, 0, 2))      # M:496-497 view-major
 
         Bf.zero_phase("fwd")
-        # masked rows of view 0 as an index list (M:569); done first so that its error flag is back on the host early (see _post_mask_err)
-        n_per = self._masked_per_sample(vis_mask_pos)
-        n_m = Bsz * n_per
+        # masked rows of view 0 as an index list (M:569); done first so that its error flag is back on the host early (see _post_mask_err).
+        # only_mim_on_ori_img False (M:571-575): the masked rows of BOTH views -- the mask buffer is view-major like the token rows, so the
+        # same kernel over 2B "samples" yields the indices of view 0 followed by those of view 1.
+        views = 1 if only_mim_on_ori_img else 2
+        n_per = self._masked_per_sample(vis_mask_pos, views)
+        n_m = views * Bsz * n_per
         idx = Bf.get("dec.idx", (max(n_m, 1),), torch.int32)
         err = Bf.zeroed("dec.err", (1,), torch.int32, "fwd")
-        call("dig_mask_to_index", mask_u8, idx, err, Bsz, n_per)
+        call("dig_mask_to_index", mask_u8, idx, err, views * Bsz, n_per)
         self._post_mask_err(err)
         # bf16 shadows of the online weights + fused qkv bias
         cur = torch.cuda.current_stream()
@@ -599,7 +600,7 @@ class PretrainStep:
                           idx=idx, n_m=n_m, g0=g0, t1=t1, t2=t2, t3=t3, dmean=dmean, drstd=drstd, pooled=pooled)
         contra = res[:, 0].sum()
         accs = res[:, 1:3].clone()      # [[q1_acc1, q1_acc5], [q2_acc1, q2_acc5]]
-        return contra, vis.view(Bsz, n_per, 48), accs
+        return contra, vis.view(views * Bsz, n_per, 48), accs      # both views: view 0's samples, then view 1's
 
     def _post_mask_err(self, err):
         """The number of masked patches per sample is validated on the host for the first batch of a shape only (a blocking read); every
@@ -619,13 +620,13 @@ class PretrainStep:
             if int(self._mask_err[1][0]) != 0:
                 raise ops.DigError("the previous batch did not mask the same number of patches in every sample (masking_generator.py:20)")
 
-    def _masked_per_sample(self, vis_mask_pos):
-        key = tuple(vis_mask_pos.shape)
+    def _masked_per_sample(self, vis_mask_pos, views=1):
+        key = tuple(vis_mask_pos.shape) + (views,)
         if key not in self._n_masked:
-            cnt = vis_mask_pos[:, 0].sum(dim=1)
-            n = int(cnt[0].item())
+            cnt = vis_mask_pos[:, :views].sum(dim=2)
+            n = int(cnt[0, 0].item())
             if not bool((cnt == n).all().item()):
-                raise ops.DigError("every sample must mask the same number of patches (masking_generator.py:20)")
+                raise ops.DigError("every sample (and view) must mask the same number of patches (masking_generator.py:20)")
             self._n_masked[key] = n
         return self._n_masked[key]
 
@@ -826,5 +827,7 @@ def run_model(step, image, aug_image, vis_mask_pos, m, only_mim_on_ori_img):
         contra, vis, accs = _PretrainFn.apply(step, image, aug_image, vis_mask_pos, m, only_mim_on_ori_img, *params)
     else:
         contra, vis, accs = step.forward(image, aug_image, vis_mask_pos, m, only_mim_on_ori_img)
+    B = image.shape[0]
+    vis_out = [vis] if only_mim_on_ori_img else [vis[:B], vis[B:]]          # M:566-575
     return {"contra_loss": contra, "q1_acc1": accs[0, 0:1], "q1_acc5": accs[0, 1:2], "q2_acc1": accs[1, 0:1],
-            "q2_acc5": accs[1, 1:2], "vis_out": [vis]}
+            "q2_acc5": accs[1, 1:2], "vis_out": vis_out}

@@ -270,14 +270,16 @@ def build_targets(images, mask_bvn, only_mim_on_ori_img=True, patch_size=PATCH, 
 
 
 def step_losses(sd, images, aug_images, mask_bvn, m, heads, w_contrast=0.1, w_pixel=1.0, T=0.2,
-                num_windows=4, rank=0, gather=None, taps=None):
-    """E:76-146 for one batch: zero view-1 mask, targets, forward, weighted loss."""
+                num_windows=4, rank=0, gather=None, taps=None, only_mim_on_ori_img=True):
+    """E:76-146 for one batch: zero view-1 mask (only_mim_on_ori_img), targets, forward, weighted loss; with only_mim_on_ori_img False
+    every view's decoder output is compared with the masked patches of the ORIGINAL image, weighted 1/num_view (E:137-141)."""
     mask_bvn = mask_bvn.clone()
-    mask_bvn[:, 1, :] = False                                                           # E:103-104
-    labels = build_targets(images, mask_bvn, True)
-    out = moco_vit_forward(sd, images, aug_images, mask_bvn, m, heads, T, num_windows, True, rank,
+    if only_mim_on_ori_img:
+        mask_bvn[:, 1, :] = False                                                       # E:103-104
+    labels = build_targets(images, mask_bvn, only_mim_on_ori_img)
+    out = moco_vit_forward(sd, images, aug_images, mask_bvn, m, heads, T, num_windows, only_mim_on_ori_img, rank,
                            gather, taps)
-    loss_pixel = Fn.mse_loss(out["vis_out"][0], labels[0], reduction="mean")            # E:141
+    loss_pixel = sum(Fn.mse_loss(o, l, reduction="mean") for o, l in zip(out["vis_out"], labels)) / len(labels)   # E:137-141
     loss = out["contra_loss"] * w_contrast + loss_pixel * w_pixel                       # E:122, E:143
     return loss, out, loss_pixel
 

@@ -44,6 +44,31 @@ def run_step(model, g):
     return out, lpix, loss
 
 
+def test_step_with_both_views_masked_matches_reference_golden():
+    """--only_mim_on_ori_img 0 (M:571-575, E:137-141): the second view keeps its mask, the pixel head decodes the masked rows of both views
+    and both are compared with the ORIGINAL image's patches, 1/2 each -- against the fixture of the unmodified reference."""
+    from oracle import restatement as R
+    from dig_b200.engine import masked_pixel_mse
+    g = torch.load(os.path.join(GOLD, "ref_step_tiny_b4_bothviews.pt"), weights_only=False)
+    model = make(g["model"]).cuda()
+    img, aug, mask = R.synthetic_batch(g["B"], seed=g["seed_data"])
+    mk = mask.bool().cuda()
+    out = model(img.cuda(), aug.cuda(), mk, g["m"], False)
+    assert len(out["vis_out"]) == 2
+    lpix = sum(masked_pixel_mse(v, img.cuda(), mk[:, i]) for i, v in enumerate(out["vis_out"])) * 0.5
+    loss = out["contra_loss"] * 0.1 + lpix
+    loss.backward()
+    assert float(lpix) == pytest.approx(g["loss_pixel"], rel=1e-3) and float(loss) == pytest.approx(g["loss"], rel=1e-3)
+    assert float(out["contra_loss"]) == pytest.approx(g["contra_loss"], rel=5e-3)
+    for o, ref in zip(out["vis_out"], g["vis_out_all"]):
+        assert o.shape == ref.shape and torch.allclose(o.cpu(), ref, atol=3e-2)
+    named = dict(model.named_parameters())
+    for n in ("pix_decoder.4.weight", "pix_decoder.0.weight", "encoder.mask_token"):
+        assert float(named[n].grad.norm()) == pytest.approx(g["grad_norms"][n], rel=4e-2), n
+    tot = sum(float(p.grad.float().pow(2).sum()) for p in model.parameters() if p.grad is not None) ** 0.5
+    assert tot == pytest.approx(sum(v ** 2 for v in g["grad_norms"].values()) ** 0.5, rel=5e-2)
+
+
 @pytest.mark.parametrize("tag,tol_contra", [("small_b2", 5e-3), ("small_b8", 1e-3), ("base_b2", 5e-3)])
 def test_step_matches_reference_golden(tag, tol_contra):
     g = torch.load(os.path.join(GOLD, "ref_step_%s.pt" % tag), weights_only=False)

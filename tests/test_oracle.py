@@ -46,6 +46,25 @@ def test_oracle_reproduces_reference_golden(tag):
         assert torch.allclose(sd[k].detach(), ref, rtol=1e-3, atol=1e-5), k
 
 
+def test_oracle_reproduces_reference_golden_with_both_views_masked():
+    """--only_mim_on_ori_img 0 (M:571-575, E:137-141): the pixel head on both views, both compared with the original image's patches."""
+    g = torch.load(os.path.join(GOLD, "ref_step_tiny_b4_bothviews.pt"), weights_only=False)
+    assert g["only_mim"] is False and len(g["vis_out_all"]) == 2
+    sd, heads = holder_state(g["model"])
+    names = R.trainable_names(sd)
+    for n in names:
+        sd[n] = sd[n].requires_grad_(True)
+    img, aug, mask = R.synthetic_batch(g["B"], seed=g["seed_data"])
+    loss, out, lpix = R.step_losses(sd, img, aug, mask, g["m"], heads, only_mim_on_ori_img=False)
+    assert float(out["contra_loss"]) == pytest.approx(g["contra_loss"], rel=2e-5)
+    assert float(lpix) == pytest.approx(g["loss_pixel"], rel=2e-5) and float(loss) == pytest.approx(g["loss"], rel=2e-5)
+    for o, ref in zip(out["vis_out"], g["vis_out_all"]):
+        assert torch.allclose(o, ref, atol=2e-5, rtol=1e-4)
+    gd = dict(zip(names, torch.autograd.grad(loss, [sd[n] for n in names], allow_unused=True)))
+    for n, ref in g["grad_norms"].items():
+        assert float(gd[n].norm()) == pytest.approx(ref, rel=5e-3, abs=1e-7), n
+
+
 def test_known_answer_of_survey():
     """contra 1.6791600, pixel 0.3883830, total 0.5562990 for ViT-S, B=2, seeds (0, 1), m=0.99."""
     g = torch.load(os.path.join(GOLD, "ref_step_small_b2.pt"), weights_only=False)
