@@ -167,11 +167,16 @@ def get(device, key_table_bytes):
         return None
     c = _comm.get("default")
     if c is None or (c.ok and c.key_table_bytes < key_table_bytes):
+        keep = []
         if c is not None:
             torch.cuda.synchronize()
             dist.barrier()
+            # a larger key table means a new workspace (collective); the shared gradient buffers handed out by alloc_shared stay mapped --
+            # models hold tensors on them -- and move to the new communicator (flags and epochs restart from zero on every rank alike)
+            keep, c._shared = c._shared, []
             c.close()
         c = PeerComm(device, key_table_bytes)
+        c._shared.extend(keep)
         _comm["default"] = c
         if not c.ok and dist.get_rank() == 0:
             print("dig_b200: NVLink peer-memory exchanges unavailable (%s); using torch.distributed collectives" % c.error)

@@ -1,9 +1,9 @@
 #!/bin/bash
-# regression + bench round on one GPU
+# regression + bench round on one GPU: the GPU test suite, smoke, the default bench line
 cd /root/repo; mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -4
-timeout 200 python scripts/gemm_ab.py "proj fwd" 2>&1 | tail -2
-for pf in 0 1; do
-DIG_PREFETCH=$pf DIG_BENCH_VIT_BASE=0 DIG_BENCH_FINETUNE=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras 2>&1 | tail -1 > gpurun_out/bench_pf$pf.json
-python -c "import json; d=json.loads(open('gpurun_out/bench_pf$pf.json').read()); print('PREFETCH=$pf ms/step', d['ms_per_step'], 'e2e', d['e2e'])"
-done
+timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py > gpurun_out/bench_final.log 2> gpurun_out/bench_final.err
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_final.log').read().strip().splitlines()[-1])
+print('ms/step', round(d['ms_per_step'],3), 'crops/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'roofline', round(d['roofline']['frac'],3), 'parity loss_rel', d['parity']['loss_rel'], 'vit_base', round(d['vit_base']['value']), 'finetune', round(d['finetune']['value']), d['clocks'])" || tail -5 gpurun_out/bench_final.err
