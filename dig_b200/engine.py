@@ -154,7 +154,10 @@ def train_one_epoch(model, teacher_model, teacher_model_without_ddp, data_loader
             log_writer.update(grad_norm=packed[7], head="opt")
             log_writer.set_step()
 
-    feed = data_loader if os.environ.get("DIG_PREFETCH", "1") == "0" else _DevicePrefetch(data_loader, device)
+    # measured: one GPU 22.46 -> 22.15 ms/step with the prefetch; two GPUs 23.03 ms without against 23.38 ms with it (the exchanges with the
+    # peer already cover the copy there), so it defaults to on for a single process only (DIG_PREFETCH=0 / 1 overrides)
+    prefetch = os.environ.get("DIG_PREFETCH", "1" if utils.get_world_size() == 1 else "0") != "0"
+    feed = _DevicePrefetch(data_loader, device) if prefetch else data_loader
     for step, (batch, text, text_lens) in enumerate(metric_logger.log_every(feed, print_freq, header)):
         it = start_steps + step
         if lr_schedule_values is not None or wd_schedule_values is not None:                      # E:60-66
